@@ -1,0 +1,156 @@
+/*
+ * kdot.h -- C ABI of libkdot.so: the B200-native optimal-transport knowledge-distillation path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: its boundary is the
+ * Python call chain  KDPoseLoss.__call__ -> KDObjectSpaceLoss -> kd_loss_2d -> geomloss.SamplesLoss
+ * (/root/reference/losses/kd_loss.py:111,40,86 ; losses/loss_libs.py:1,47) and
+ * PostProcessorKD.forward (/root/reference/postprocess/postprocess_kd.py:61).  Each entry point below
+ * names the reference code it replaces.  Signatures use plain pointers and sizes only (no torch types);
+ * the Python host side (kd_6d_pose_adlp_b200/) binds them with ctypes.
+ *
+ * Conventions
+ *   - all device pointers are caller-owned, contiguous, 16-byte aligned fp32 / int32 buffers;
+ *   - every call is asynchronous on `cuda_stream` (a cudaStream_t passed as void*), allocates nothing
+ *     and returns 0 on success or a KDOT_E_* code (kdot_last_error() gives the text);
+ *   - B = OT slots per cell (8 keypoints for WDRNet+), D = dims of one local prediction (2).
+ */
+#ifndef KDOT_H_
+#define KDOT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDOT_VERSION 100
+
+enum {
+  KDOT_OK = 0,
+  KDOT_E_BADARG = 1,      /* NULL pointer, negative size, unsupported p / D / layout            */
+  KDOT_E_TOOLARGE = 2,    /* problem does not fit the kernel's shared-memory plan                */
+  KDOT_E_WORKSPACE = 3,   /* workspace smaller than kdot_workspace_bytes()                        */
+  KDOT_E_CUDA = 4,        /* launch / runtime failure                                             */
+  KDOT_E_NODEVICE = 5     /* no CUDA device -- there is NO CPU fallback                           */
+};
+
+/* Layout of the cell arrays. */
+enum {
+  KDOT_LAYOUT_CELL_MAJOR = 0, /* xs[cell][slot][D], ws[cell][slot]: the reference's flat layout,
+                                 losses/kd_loss.py:50,83 (pred_xy.view(-1,8,2), s_cls (sumN,8))   */
+  KDOT_LAYOUT_SLOT_MAJOR = 1  /* xs[slot][cell][D], ws[slot][cell]: SamplesLoss' (B,N,D)/(B,N)
+                                 batch layout, losses/loss_libs.py:41-47; requires nimg == 1      */
+};
+
+/* per-image status written to valid[] */
+enum {
+  KDOT_IMG_SKIPPED = 0,     /* N == 0 or M == 0: skipped like losses/loss_libs.py:25-28          */
+  KDOT_IMG_OK = 1,
+  KDOT_IMG_DEGENERATE = -1, /* zero diameter: geomloss' epsilon_schedule would raise; loss = NaN */
+  KDOT_IMG_TOO_MANY_ROUNDS = -2 /* eps schedule longer than KDOT_MAX_ROUNDS; loss = NaN           */
+};
+
+#define KDOT_MAX_ROUNDS 1024
+
+/*
+ * Fused optimal-transport distillation loss, forward + analytic backward, whole mini-batch.
+ *
+ * Replaces, per image i with N_i = cu_n[i+1]-cu_n[i] student and M_i teacher cells:
+ *   - the in-place normalisation  xy[:,0] /= w ; xy[:,1] /= h        (losses/loss_libs.py:8-12)
+ *     when normalize != 0 (requires D == 2); xs AND xt are overwritten with the normalised values;
+ *   - the per-image split / transposes / SamplesLoss(...).sum() loop   (losses/loss_libs.py:22-50);
+ *   - geomloss.SamplesLoss("sinkhorn", p, blur, scaling, reach) on the tensorized backend, i.e. the
+ *     four cost matrices, max_diameter, the float64 epsilon schedule, the symmetrised log-domain
+ *     Sinkhorn loop, the last extrapolation and the debiased (un)balanced cost (geomloss 0.2.4;
+ *     constructed at losses/kd_loss.py:26-30) -- none of the N x M matrices is materialised;
+ *   - autograd's backward of all of the above w.r.t. the student points and masses.
+ *
+ * ws / wt may be NULL: uniform 1/N_i, 1/M_i masses (losses/loss_libs.py:49, --weightedOT false).
+ * reach < 0 selects balanced OT (geomloss reach=None).  Only p == 2 is implemented.
+ *
+ * Outputs
+ *   loss_per_img [nimg]    sum over the B slots of the Sinkhorn divergence (the `.sum()` of
+ *                          loss_libs.py:47); 0 for skipped images
+ *   loss_per_slot[nimg*B]  optional (may be NULL): the (B,) vector SamplesLoss itself returns
+ *   valid        [nimg]    KDOT_IMG_* status
+ *   grad_xs, grad_ws       d(loss_per_img)/d(xs), d/d(ws), same layout as xs / ws; the xs gradient
+ *                          is w.r.t. the UN-normalised input when normalize != 0 (includes 1/w, 1/h)
+ *                          (grad_ws is written even when ws == NULL; it may be NULL)
+ *   nits_per_img [nimg]    optional: len(eps_s) of geomloss' schedule (parity / debugging)
+ * The caller applies the reduction over images (losses/kd_loss.py:99-101 divides the sum of the
+ * non-skipped images by their count).
+ */
+int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt,
+                          const int32_t* cu_n, const int32_t* cu_m, int nimg, int B, int D,
+                          int max_n, int max_m, int layout,
+                          float p, float blur, float reach, float scaling,
+                          float w, float h, int normalize,
+                          float* loss_per_img, float* loss_per_slot, int32_t* valid,
+                          float* grad_xs, float* grad_ws, int32_t* nits_per_img,
+                          void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Bytes of device scratch kdot_sinkhorn_fwd_bwd needs for these bounds (0 is a valid answer). */
+size_t kdot_workspace_bytes(int nimg, int max_n, int max_m, int B, int D);
+
+/*
+ * Host-buffer convenience around kdot_sinkhorn_fwd_bwd for callers that hold NumPy / C arrays
+ * (what `bench.py` times as the end-to-end number): packs the inputs into a pinned staging area,
+ * one H2D copy, the fused kernel, one D2H copy, stream synchronise, unpack.  All pointers are HOST
+ * pointers; pos_n / pos_m are the per-image cell counts (pos_per_img, pos_per_img_t of
+ * losses/kd_loss.py:74-76).  xs_h / xt_h are overwritten with the normalised values only when
+ * write_back_normalized != 0.  The context owns device + pinned memory sized at creation.
+ */
+typedef struct kdot_host_ctx kdot_host_ctx;
+kdot_host_ctx* kdot_host_ctx_create(int device, int max_img, int max_cells_s, int max_cells_t, int B, int D);
+void kdot_host_ctx_destroy(kdot_host_ctx* ctx);
+int kdot_sinkhorn_fwd_bwd_host(kdot_host_ctx* ctx, float* xs_h, const float* ws_h, float* xt_h,
+                               const float* wt_h, const int32_t* pos_n, const int32_t* pos_m, int nimg,
+                               float p, float blur, float reach, float scaling, float w, float h,
+                               int normalize, int write_back_normalized,
+                               float* loss_per_img_h, int32_t* valid_h, float* grad_xs_h,
+                               float* grad_ws_h, int32_t* nits_h);
+/* bytes moved by the last host call (for bench.py's e2e accounting) */
+void kdot_host_ctx_last_traffic(const kdot_host_ctx* ctx, size_t* h2d_bytes, size_t* d2h_bytes);
+
+/*
+ * Teacher knowledge extraction: segmentation-weighted cell voting / selection, all images and all
+ * classes in one launch.  Replaces the index-producing part of
+ *   PostProcessorKD.forward_for_single_feature_map  (postprocess/postprocess_kd.py:22-59)
+ *   PostProcessorKD.pose_infer_ml                   (postprocess/postprocess_kd.py:99-156)
+ * i.e. sigmoid > th candidates, per-level arg-max, box size of the running-best cell, the per-level
+ * cell budget nk = int(positive_num * softmax-like(-lambda * log2(size/anchor)^2) + 0.5), and the
+ * per-level top-min(valid, nk) by score.  RANSAC-EPnP (postprocess_kd.py:191) stays on the host.
+ *
+ * Inputs (device): cls_lvl[l] -> (nimg, C, H_l, W_l) logits, reg_lvl[l] -> (nimg, C*16, H_l, W_l);
+ * hw_lvl[l] = H_l * W_l and stride_lvl[l], anchor size per level (host arrays); anchor_sizes_all
+ * is the FULL cfg list (its sum normalises nk even when nlvl is shorter: postprocess_kd.py:143).
+ * Outputs (device), per (image, class) pair q = img * C + cls, capacity `cap` cells:
+ *   sel_count[q]                number of selected cells (0 when the class has no candidate)
+ *   sel_level[q*cap + k], sel_loc[q*cap + k]   level and h*W+w index of the k-th selected cell,
+ *                               level by level, descending score inside a level (topk order)
+ *   sel_score[q*cap + k]        sqrt(sigmoid(logit))  (postprocess_kd.py:57)
+ *   sel_kpts [(q*cap + k)*16]   decoded keypoints [x0..x7, y0..y7] in crop pixels (model.py:144-154)
+ *   nk[q*nsizes + l]            per-level budget; valid_cnt[q*nlvl + l] candidates per level
+ *   best[q*2 + {0,1}]           level / loc of the highest-confidence cell
+ */
+int kdot_select_cells(const float* const* cls_lvl, const float* const* reg_lvl, const int32_t* hw_lvl,
+                      const int32_t* w_lvl, const float* stride_lvl, int nlvl,
+                      const float* anchor_sizes_all, int nsizes,
+                      int nimg, int C, float th, int positive_num, float positive_lambda, int cap,
+                      int32_t* sel_count, int32_t* sel_level, int32_t* sel_loc, float* sel_score,
+                      float* sel_kpts, int32_t* nk, int32_t* valid_cnt, int32_t* best,
+                      void* cuda_stream);
+
+/* Diagnostics */
+const char* kdot_last_error(void);
+int kdot_version(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+unsigned long long kdot_launch_count(void);
+/* FP32 FMA-chain micro-benchmark: returns measured TFLOP/s of the device (roofline denominator) */
+double kdot_measure_fp32_peak_tflops(int device, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDOT_H_ */

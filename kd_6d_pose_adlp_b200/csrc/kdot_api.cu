@@ -1,0 +1,321 @@
+// C-ABI entry points of libkdot.so (see include/kdot.h for the contract and the reference citations).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kdot_common.cuh"
+
+namespace kdot {
+cudaError_t launch_small(const SinkhornParams& prm, cudaStream_t stream);
+cudaError_t launch_tiled(const SinkhornParams& prm, int max_n, int max_m, cudaStream_t stream, size_t smem_limit,
+                         bool* too_large);
+size_t tiled_smem_bytes(int max_n, int max_m);
+
+static thread_local std::string g_err;
+static std::atomic<unsigned long long> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+static int fail_cuda(cudaError_t e, const char* where) {
+  g_err = std::string(where) + ": " + cudaGetErrorString(e);
+  return KDOT_E_CUDA;
+}
+void count_launches(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static bool small_path(int max_n, int max_m, int B) { return max_n + max_m <= 64 && B <= 16; }
+
+struct WorkspacePlan {
+  size_t off_sched, off_rounds, off_slot, off_ctr, total;
+};
+static WorkspacePlan plan_workspace(int nimg, int B) {
+  WorkspacePlan w;
+  size_t o = 0;
+  w.off_sched = o;  o = align_up(o + (size_t)nimg * KDOT_MAX_ROUNDS * sizeof(RoundConst), 256);
+  w.off_rounds = o; o = align_up(o + (size_t)nimg * sizeof(int32_t), 256);
+  w.off_slot = o;   o = align_up(o + (size_t)nimg * B * sizeof(float), 256);
+  w.off_ctr = o;    o = align_up(o + (size_t)nimg * sizeof(unsigned int), 256);
+  w.total = o;
+  return w;
+}
+
+static size_t device_smem_limit() {
+  static size_t lim = 0;
+  if (lim == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess)
+      lim = (size_t)v;
+  }
+  return lim;
+}
+}  // namespace kdot
+
+using namespace kdot;
+
+extern "C" {
+
+const char* kdot_last_error(void) { return g_err.c_str(); }
+int kdot_version(void) { return KDOT_VERSION; }
+unsigned long long kdot_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t kdot_workspace_bytes(int nimg, int max_n, int max_m, int B, int D) {
+  (void)D;
+  if (nimg <= 0 || small_path(max_n, max_m, B)) return 0;
+  return plan_workspace(nimg, B).total;
+}
+
+int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt, const int32_t* cu_n,
+                          const int32_t* cu_m, int nimg, int B, int D, int max_n, int max_m, int layout, float p,
+                          float blur, float reach, float scaling, float w, float h, int normalize,
+                          float* loss_per_img, float* loss_per_slot, int32_t* valid, float* grad_xs, float* grad_ws,
+                          int32_t* nits_per_img, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  if (nimg == 0) return KDOT_OK;
+  if (nimg < 0 || B <= 0 || max_n < 0 || max_m < 0) return fail(KDOT_E_BADARG, "negative size");
+  if (!xs || !xt || !cu_n || !cu_m || !loss_per_img || !valid || !grad_xs)
+    return fail(KDOT_E_BADARG, "NULL required pointer");
+  if (D != 2) return fail(KDOT_E_BADARG, "only D == 2 is implemented by this build");
+  if (p != 2.0f) return fail(KDOT_E_BADARG, "only p == 2 is implemented");
+  if (!(blur > 0.f) || !(scaling > 0.f && scaling < 1.f)) return fail(KDOT_E_BADARG, "blur > 0 and 0 < scaling < 1 required");
+  if (layout != KDOT_LAYOUT_CELL_MAJOR && layout != KDOT_LAYOUT_SLOT_MAJOR) return fail(KDOT_E_BADARG, "bad layout");
+  if (layout == KDOT_LAYOUT_SLOT_MAJOR && nimg != 1) return fail(KDOT_E_BADARG, "slot-major layout requires nimg == 1");
+  if (normalize && !(w > 0.f && h > 0.f)) return fail(KDOT_E_BADARG, "normalize needs w, h > 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(KDOT_E_NODEVICE, "no CUDA device: libkdot has no CPU fallback");
+
+  SinkhornParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.xs = xs; prm.ws = ws; prm.xt = xt; prm.wt = wt;
+  prm.cu_n = cu_n; prm.cu_m = cu_m;
+  prm.nimg = nimg; prm.B = B;
+  if (layout == KDOT_LAYOUT_CELL_MAJOR) {
+    prm.s_cell_n = B; prm.s_slot_n = 1; prm.s_cell_m = B; prm.s_slot_m = 1;
+  } else {  // single image: N == max_n, M == max_m
+    prm.s_cell_n = 1; prm.s_slot_n = max_n; prm.s_cell_m = 1; prm.s_slot_m = max_m;
+  }
+  prm.p = (double)p; prm.blur = (double)blur; prm.scaling = (double)scaling;
+  prm.rho = reach < 0.f ? -1.0 : pow((double)reach, (double)p);
+  prm.w = w; prm.h = h; prm.normalize = normalize;
+  prm.loss_per_img = loss_per_img; prm.loss_per_slot = loss_per_slot; prm.valid = valid;
+  prm.grad_xs = grad_xs; prm.grad_ws = grad_ws; prm.nits_per_img = nits_per_img;
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+
+  if (small_path(max_n, max_m, B)) {
+    cudaError_t e = launch_small(prm, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "kdot_small_kernel");
+    count_launches(1);
+    return KDOT_OK;
+  }
+  const WorkspacePlan wp = plan_workspace(nimg, B);
+  if (!workspace || workspace_bytes < wp.total) return fail(KDOT_E_WORKSPACE, "workspace too small (see kdot_workspace_bytes)");
+  char* base = (char*)workspace;
+  prm.sched = (RoundConst*)(base + wp.off_sched);
+  prm.sched_rounds = (int32_t*)(base + wp.off_rounds);
+  prm.slot_loss = (float*)(base + wp.off_slot);
+  prm.done_ctr = (unsigned int*)(base + wp.off_ctr);
+  bool too_large = false;
+  cudaError_t e = launch_tiled(prm, max_n, max_m, stream, device_smem_limit(), &too_large);
+  if (too_large) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "clouds of %d + %d cells need %zu B of shared memory (limit %zu)", max_n, max_m,
+             tiled_smem_bytes(max_n, max_m), device_smem_limit());
+    return fail(KDOT_E_TOOLARGE, buf);
+  }
+  if (e != cudaSuccess) return fail_cuda(e, "kdot_tiled_kernel");
+  count_launches(2);
+  return KDOT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-buffer path
+// ---------------------------------------------------------------------------------------------------------
+struct kdot_host_ctx {
+  int device, max_img, max_s, max_t, B, D;
+  cudaStream_t stream;
+  char* pin_in; char* pin_out; char* dev_in; char* dev_out; char* dev_ws;
+  size_t cap_in, cap_out, cap_ws;
+  size_t last_h2d, last_d2h;
+};
+
+kdot_host_ctx* kdot_host_ctx_create(int device, int max_img, int max_cells_s, int max_cells_t, int B, int D) {
+  if (max_img <= 0 || max_cells_s < 0 || max_cells_t < 0 || B <= 0 || D <= 0) {
+    g_err = "kdot_host_ctx_create: bad sizes";
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    g_err = "kdot_host_ctx_create: cudaSetDevice failed (no CUDA device: libkdot has no CPU fallback)";
+    return nullptr;
+  }
+  kdot_host_ctx* c = new kdot_host_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device; c->max_img = max_img; c->max_s = max_cells_s; c->max_t = max_cells_t; c->B = B; c->D = D;
+  const size_t pts = (size_t)(max_cells_s + max_cells_t) * B;
+  c->cap_in = align_up(pts * (D + 1) * sizeof(float) + 2 * (size_t)(max_img + 1) * sizeof(int32_t) + 1024, 256);
+  c->cap_out = align_up((size_t)max_img * 3 * sizeof(float) + (size_t)max_cells_s * B * (D + 1) * sizeof(float) +
+                            pts * D * sizeof(float) + 1024, 256);
+  c->cap_ws = plan_workspace(max_img, B).total;
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaMallocHost((void**)&c->pin_in, c->cap_in) == cudaSuccess &&
+            cudaMallocHost((void**)&c->pin_out, c->cap_out) == cudaSuccess &&
+            cudaMalloc((void**)&c->dev_in, c->cap_in) == cudaSuccess &&
+            cudaMalloc((void**)&c->dev_out, c->cap_out) == cudaSuccess &&
+            cudaMalloc((void**)&c->dev_ws, c->cap_ws) == cudaSuccess;
+  if (!ok) {
+    g_err = std::string("kdot_host_ctx_create: ") + cudaGetErrorString(cudaGetLastError());
+    kdot_host_ctx_destroy(c);
+    return nullptr;
+  }
+  return c;
+}
+
+void kdot_host_ctx_destroy(kdot_host_ctx* c) {
+  if (!c) return;
+  if (c->pin_in) cudaFreeHost(c->pin_in);
+  if (c->pin_out) cudaFreeHost(c->pin_out);
+  if (c->dev_in) cudaFree(c->dev_in);
+  if (c->dev_out) cudaFree(c->dev_out);
+  if (c->dev_ws) cudaFree(c->dev_ws);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+void kdot_host_ctx_last_traffic(const kdot_host_ctx* c, size_t* h2d, size_t* d2h) {
+  if (h2d) *h2d = c ? c->last_h2d : 0;
+  if (d2h) *d2h = c ? c->last_d2h : 0;
+}
+
+int kdot_sinkhorn_fwd_bwd_host(kdot_host_ctx* c, float* xs_h, const float* ws_h, float* xt_h, const float* wt_h,
+                               const int32_t* pos_n, const int32_t* pos_m, int nimg, float p, float blur, float reach,
+                               float scaling, float w, float h, int normalize, int write_back_normalized,
+                               float* loss_per_img_h, int32_t* valid_h, float* grad_xs_h, float* grad_ws_h,
+                               int32_t* nits_h) {
+  if (!c) return fail(KDOT_E_BADARG, "NULL context");
+  if (nimg == 0) return KDOT_OK;
+  if (nimg < 0 || nimg > c->max_img || !xs_h || !xt_h || !pos_n || !pos_m || !loss_per_img_h || !valid_h || !grad_xs_h)
+    return fail(KDOT_E_BADARG, "bad host arguments");
+  const int B = c->B, D = c->D;
+  long long sn = 0, sm = 0;
+  int max_n = 0, max_m = 0;
+  for (int i = 0; i < nimg; ++i) {
+    if (pos_n[i] < 0 || pos_m[i] < 0) return fail(KDOT_E_BADARG, "negative cell count");
+    sn += pos_n[i]; sm += pos_m[i];
+    if (pos_n[i] > max_n) max_n = pos_n[i];
+    if (pos_m[i] > max_m) max_m = pos_m[i];
+  }
+  if (sn > c->max_s || sm > c->max_t) return fail(KDOT_E_BADARG, "more cells than the context was created for");
+  if (cudaSetDevice(c->device) != cudaSuccess) return fail(KDOT_E_CUDA, "cudaSetDevice");
+
+  // ---- pack inputs into pinned staging: xs | xt | ws | wt | cu_n | cu_m (each 16-byte aligned) ----
+  size_t o = 0;
+  const size_t b_xs = (size_t)sn * B * D * sizeof(float), b_xt = (size_t)sm * B * D * sizeof(float);
+  const size_t b_ws = (size_t)sn * B * sizeof(float), b_wt = (size_t)sm * B * sizeof(float);
+  const size_t o_xs = o; o = align_up(o + b_xs, 16);
+  const size_t o_xt = o; o = align_up(o + b_xt, 16);
+  const size_t o_ws = o; o = align_up(o + (ws_h ? b_ws : 0), 16);
+  const size_t o_wt = o; o = align_up(o + (wt_h ? b_wt : 0), 16);
+  const size_t o_cn = o; o = align_up(o + (size_t)(nimg + 1) * sizeof(int32_t), 16);
+  const size_t o_cm = o; o = align_up(o + (size_t)(nimg + 1) * sizeof(int32_t), 16);
+  const size_t in_bytes = o;
+  memcpy(c->pin_in + o_xs, xs_h, b_xs);
+  memcpy(c->pin_in + o_xt, xt_h, b_xt);
+  if (ws_h) memcpy(c->pin_in + o_ws, ws_h, b_ws);
+  if (wt_h) memcpy(c->pin_in + o_wt, wt_h, b_wt);
+  int32_t* cn = (int32_t*)(c->pin_in + o_cn);
+  int32_t* cm = (int32_t*)(c->pin_in + o_cm);
+  cn[0] = 0; cm[0] = 0;
+  for (int i = 0; i < nimg; ++i) { cn[i + 1] = cn[i] + pos_n[i]; cm[i + 1] = cm[i] + pos_m[i]; }
+
+  // ---- outputs: loss | valid | nits | grad_xs | grad_ws ----
+  size_t q = 0;
+  const size_t q_loss = q; q = align_up(q + (size_t)nimg * sizeof(float), 16);
+  const size_t q_valid = q; q = align_up(q + (size_t)nimg * sizeof(int32_t), 16);
+  const size_t q_nits = q; q = align_up(q + (size_t)nimg * sizeof(int32_t), 16);
+  const size_t q_gx = q; q = align_up(q + b_xs, 16);
+  const size_t q_gw = q; q = align_up(q + b_ws, 16);
+  const size_t out_bytes = q;
+
+  cudaError_t e = cudaMemcpyAsync(c->dev_in, c->pin_in, in_bytes, cudaMemcpyHostToDevice, c->stream);
+  if (e != cudaSuccess) return fail_cuda(e, "H2D");
+  int rc = kdot_sinkhorn_fwd_bwd((float*)(c->dev_in + o_xs), ws_h ? (const float*)(c->dev_in + o_ws) : nullptr,
+                                 (float*)(c->dev_in + o_xt), wt_h ? (const float*)(c->dev_in + o_wt) : nullptr,
+                                 (const int32_t*)(c->dev_in + o_cn), (const int32_t*)(c->dev_in + o_cm), nimg, B, D,
+                                 max_n, max_m, KDOT_LAYOUT_CELL_MAJOR, p, blur, reach, scaling, w, h, normalize,
+                                 (float*)(c->dev_out + q_loss), nullptr, (int32_t*)(c->dev_out + q_valid),
+                                 (float*)(c->dev_out + q_gx), (float*)(c->dev_out + q_gw),
+                                 (int32_t*)(c->dev_out + q_nits), c->dev_ws, c->cap_ws, c->stream);
+  if (rc != KDOT_OK) return rc;
+  e = cudaMemcpyAsync(c->pin_out, c->dev_out, out_bytes, cudaMemcpyDeviceToHost, c->stream);
+  if (e != cudaSuccess) return fail_cuda(e, "D2H");
+  size_t d2h = out_bytes;
+  if (normalize && write_back_normalized) {
+    e = cudaMemcpyAsync(c->pin_in, c->dev_in, o_ws, cudaMemcpyDeviceToHost, c->stream);  // xs | xt normalised
+    if (e != cudaSuccess) return fail_cuda(e, "D2H normalised");
+    d2h += o_ws;
+  }
+  e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) return fail_cuda(e, "stream sync");
+  memcpy(loss_per_img_h, c->pin_out + q_loss, (size_t)nimg * sizeof(float));
+  memcpy(valid_h, c->pin_out + q_valid, (size_t)nimg * sizeof(int32_t));
+  if (nits_h) memcpy(nits_h, c->pin_out + q_nits, (size_t)nimg * sizeof(int32_t));
+  memcpy(grad_xs_h, c->pin_out + q_gx, b_xs);
+  if (grad_ws_h) memcpy(grad_ws_h, c->pin_out + q_gw, b_ws);
+  if (normalize && write_back_normalized) {
+    memcpy(xs_h, c->pin_in + o_xs, b_xs);
+    memcpy(xt_h, c->pin_in + o_xt, b_xt);
+  }
+  c->last_h2d = in_bytes;
+  c->last_d2h = d2h;
+  return KDOT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FP32 FMA-chain micro-benchmark (roofline denominator measured on the box)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kdot_fma_chain_kernel(float* out, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+  float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float b = 1.0000001f, c = 1e-7f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+      a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+double kdot_measure_fp32_peak_tflops(int device, int iters) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int blocks = sms * 8, threads = 256;
+  float* out = nullptr;
+  if (cudaMalloc((void**)&out, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  kdot_fma_chain_kernel<<<blocks, threads>>>(out, iters);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    kdot_fma_chain_kernel<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = (double)blocks * threads * (double)iters * 16.0 * 8.0 * 2.0;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}
+
+}  // extern "C"

