@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""Benchmark of the OT knowledge-distillation hot path (BASELINE.json metric: KD-loss fwd+bwd images/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl kdot|reference] [--workload ape_b64|dense_b32]
+
+One "step" = one pass of the fused loss (forward + analytic backward) over one synthetic LINEMOD-ape shaped
+mini-batch.  Default workload = BASELINE.json configs[1]: ape shape (8 keypoint slots, ~10 student / ~10
+teacher cells per image), batch 64 per GPU.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
+
+* ``value``  device-resident throughput: inputs already in HBM, CUDA events around each step, L2 flushed and
+  inputs restored between steps (outside the timed events), max over ranks.
+* ``e2e``    same metric through the C ABI's host-buffer entry point (``kdot_sinkhorn_fwd_bwd_host``): pack +
+  H2D + kernel + D2H + sync every step, wall clock.
+* ``roofline``  algorithmic FLOPs of the launch / event time vs the FP32 FMA peak measured live on this GPU
+  (the path is FP32/SFU bound, not HBM bound: the N x M cost matrix never leaves registers); HBM fraction
+  reported beside it against MEASURED_PEAKS.json.
+* ``cpu_baseline``  the oracle port of the reference formulation (torch CPU ops, fp32, autograd) on a bounded
+  sample, host cores of this box.  ``--impl reference`` times only that, as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "kd_loss_fwd_bwd_images_per_sec"
+UNIT = "images/s"
+CFG = dict(p=2.0, blur=0.001, scaling=0.5, reach=0.5, w=640.0, h=480.0)
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "ape_b64": dict(nimg=64, dense=None, desc="LINEMOD-ape shape: B=8 keypoint slots, N~U{8..12} student / "
+                    "M~U{8..12} teacher cells per image (5% empty teachers), D=2, batch 64 per GPU, "
+                    "sinkhorn p=2 blur=1e-3 scaling=0.5 reach=0.5"),
+    # BASELINE.json configs[2] variant 3b: every cell of the darknet_tiny / darknet53 grids
+    "dense_b32": dict(nimg=32, dense=(1360, 1364), desc="all cells: N=1360 student / M=1364 teacher cells per "
+                      "image, B=8, D=2, batch 32 per GPU"),
+}
+
+
+def make_batch(workload, rank, nimg=None):
+    from kd_6d_pose_adlp_b200.synthetic import ot_batch
+
+    w = WORKLOADS[workload]
+    return ot_batch(nimg or w["nimg"], seed=1234 + rank, dense=w["dense"], sigma=0.05 if w["dense"] is None else 0.1)
+
+
+def algorithmic_work(batch, nits):
+    """FLOPs / exps / bytes of one step from BASELINE.md section 3 (B slots, R = nits + 2 rounds per image)."""
+    B, D = batch["xs"].shape[1], batch["xs"].shape[2]
+    flops = exps = byts = 0.0
+    for n, m, it in zip(batch["pos_per_img"], batch["pos_per_img_t"], nits):
+        if n == 0 or m == 0:
+            continue
+        R = int(it) + 2
+        flops += B * (R * (n + m) ** 2 * (3 * D + 5) + n * (n + m) * 2 * D)
+        exps += B * R * (n + m) ** 2
+        byts += 4 * B * ((n + m) * (D + 1) + n * (D + 1) + 1)
+    return flops, exps, byts
+
+
+class ClockSampler(threading.Thread):
+    """Polls SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.stop_flag, self.max_mhz = [], set(), False, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_port_images_per_sec(batch, budget_s=12.0, min_passes=2, threads=None):
+    """Times the oracle port of the reference formulation (fp32 torch CPU ops + autograd) on `batch`."""
+    import torch
+
+    from oracle import geomloss_ref, kd_loss_ref  # test infrastructure: allowed here (cpu_baseline leg only)
+
+    if threads:
+        torch.set_num_threads(threads)
+    L = geomloss_ref.SamplesLoss("sinkhorn", p=CFG["p"], blur=CFG["blur"], scaling=CFG["scaling"], reach=CFG["reach"])
+    xt0 = torch.from_numpy(batch["xt"].reshape(-1, 2))
+    wt = torch.from_numpy(batch["wt"])
+    nimg = len(batch["pos_per_img"])
+
+    def one_pass():
+        xs = torch.from_numpy(batch["xs"].reshape(-1, 2)).clone().requires_grad_(True)
+        ws = torch.from_numpy(batch["ws"]).clone().requires_grad_(True)
+        losses = kd_loss_ref.kd_loss_2d_ref(xs.clone(), xt0.clone(), ws, wt, CFG["w"], CFG["h"], "point", L, dim=2,
+                                            pos_per_img=batch["pos_per_img"], pos_per_img_t=batch["pos_per_img_t"])
+        (sum(losses) / len(losses)).backward()
+        return xs.grad
+
+    one_pass()  # warm-up
+    t0 = time.perf_counter()
+    passes = 0
+    while passes < min_passes or (time.perf_counter() - t0) < budget_s:
+        one_pass()
+        passes += 1
+        if passes >= 1000:
+            break
+    dt = time.perf_counter() - t0
+    return nimg * passes / dt, passes, dt, torch.get_num_threads()
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's formulation on the box's host cores (oracle port; geomloss itself is
+    not installable offline).  Rank 0 only."""
+    if rank != 0:
+        return
+    import torch
+
+    workload = args.workload
+    sample_img = 64 if WORKLOADS[workload]["dense"] is None else 1
+    batch = make_batch(workload, 0, nimg=sample_img)
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    from oracle import geomloss_ref, kd_loss_ref
+
+    L = geomloss_ref.SamplesLoss("sinkhorn", p=CFG["p"], blur=CFG["blur"], scaling=CFG["scaling"], reach=CFG["reach"])
+    xt0 = torch.from_numpy(batch["xt"].reshape(-1, 2))
+    wt = torch.from_numpy(batch["wt"])
+
+    def step():
+        xs = torch.from_numpy(batch["xs"].reshape(-1, 2)).clone().requires_grad_(True)
+        ws = torch.from_numpy(batch["ws"]).clone().requires_grad_(True)
+        losses = kd_loss_ref.kd_loss_2d_ref(xs.clone(), xt0.clone(), ws, wt, CFG["w"], CFG["h"], "point", L, dim=2,
+                                            pos_per_img=batch["pos_per_img"], pos_per_img_t=batch["pos_per_img_t"])
+        (sum(losses) / len(losses)).backward()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    ms = dt / args.steps * 1e3
+    value = sample_img / (ms * 1e-3)
+    sample = f"{sample_img} images of workload {workload} per step, fwd+bwd, fp32 torch CPU ops"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "desc": WORKLOADS[workload]["desc"], **CFG},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference formulation (kd_loss_2d loop + geomloss-0.2.4 restatement) on host cores; "
+                "geomloss is not installable offline, see DESIGN.md",
+    }
+    print(json.dumps(line), flush=True)
+
+
+class DeviceBench:
+    """Device-resident runner: preallocated buffers, direct C-ABI calls on the current stream."""
+
+    def __init__(self, batch, dev):
+        import torch
+
+        from kd_6d_pose_adlp_b200 import _lib
+        from kd_6d_pose_adlp_b200.ops import cu_seqlens
+
+        self.torch, self.L, self._lib = torch, _lib.lib(), _lib
+        self.dev = dev
+        self.batch = batch
+        t = lambda a: torch.from_numpy(a).to(dev)
+        self.xs0, self.xt0 = t(batch["xs"]), t(batch["xt"])
+        self.xs, self.xt = self.xs0.clone(), self.xt0.clone()
+        self.ws, self.wt = t(batch["ws"]), t(batch["wt"])
+        self.nimg = len(batch["pos_per_img"])
+        self.B, self.D = batch["xs"].shape[1], batch["xs"].shape[2]
+        self.cu_n = cu_seqlens(batch["pos_per_img"], dev)
+        self.cu_m = cu_seqlens(batch["pos_per_img_t"], dev)
+        self.max_n, self.max_m = max(batch["pos_per_img"]), max(batch["pos_per_img_t"])
+        self.loss = torch.empty(self.nimg, dtype=torch.float32, device=dev)
+        self.valid = torch.empty(self.nimg, dtype=torch.int32, device=dev)
+        self.nits = torch.empty(self.nimg, dtype=torch.int32, device=dev)
+        self.gx = torch.empty_like(self.xs)
+        self.gw = torch.empty_like(self.ws)
+        nb = int(self.L.kdot_workspace_bytes(self.nimg, self.max_n, self.max_m, self.B, self.D))
+        self.wsp = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+        self.wsp_bytes = nb
+        self.flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def restore_and_flush(self):
+        self.xs.copy_(self.xs0)
+        self.xt.copy_(self.xt0)
+        self.flush_buf.fill_(1)
+
+    def step(self):
+        torch = self.torch
+        rc = self.L.kdot_sinkhorn_fwd_bwd(
+            self.xs.data_ptr(), self.ws.data_ptr(), self.xt.data_ptr(), self.wt.data_ptr(), self.cu_n.data_ptr(),
+            self.cu_m.data_ptr(), self.nimg, self.B, self.D, self.max_n, self.max_m, 0, CFG["p"], CFG["blur"],
+            CFG["reach"], CFG["scaling"], CFG["w"], CFG["h"], 1, self.loss.data_ptr(), None, self.valid.data_ptr(),
+            self.gx.data_ptr(), self.gw.data_ptr(), self.nits.data_ptr(), self.wsp.data_ptr(), self.wsp_bytes,
+            torch.cuda.current_stream(self.dev).cuda_stream)
+        self._lib.check(rc, "kdot_sinkhorn_fwd_bwd")
+
+    def timed(self, steps, warmup, barrier):
+        torch = self.torch
+        for _ in range(warmup):
+            self.restore_and_flush()
+            self.step()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        torch.cuda.synchronize(self.dev)
+        l0 = self._lib.launch_count()
+        for e0, e1 in evs:
+            self.restore_and_flush()
+            e0.record()
+            self.step()
+            e1.record()
+        torch.cuda.synchronize(self.dev)
+        barrier()
+        launches = self._lib.launch_count() - l0
+        per = [e0.elapsed_time(e1) for e0, e1 in evs]
+        return sum(per), per, launches
+
+
+def host_e2e(batch, dev_index, steps, warmup, barrier):
+    """End to end through kdot_sinkhorn_fwd_bwd_host: host numpy buffers in, host numpy buffers out."""
+    from kd_6d_pose_adlp_b200 import _lib
+
+    L = _lib.lib()
+    nimg = len(batch["pos_per_img"])
+    B, D = batch["xs"].shape[1], batch["xs"].shape[2]
+    sn, sm = batch["xs"].shape[0], batch["xt"].shape[0]
+    ctx = L.kdot_host_ctx_create(dev_index, nimg, sn, sm, B, D)
+    if not ctx:
+        raise RuntimeError("kdot_host_ctx_create: " + L.kdot_last_error().decode())
+    xs, xt = batch["xs"].copy(), batch["xt"].copy()
+    ws, wt = batch["ws"], batch["wt"]
+    pn = np.asarray(batch["pos_per_img"], np.int32)
+    pm = np.asarray(batch["pos_per_img_t"], np.int32)
+    loss = np.empty(nimg, np.float32)
+    valid = np.empty(nimg, np.int32)
+    nits = np.empty(nimg, np.int32)
+    gx = np.empty_like(xs)
+    gw = np.empty_like(ws)
+    p = lambda a: a.ctypes.data
+
+    def step():
+        rc = L.kdot_sinkhorn_fwd_bwd_host(ctx, p(xs), p(ws), p(xt), p(wt), p(pn), p(pm), nimg, CFG["p"], CFG["blur"],
+                                          CFG["reach"], CFG["scaling"], CFG["w"], CFG["h"], 1, 0, p(loss), p(valid),
+                                          p(gx), p(gw), p(nits))
+        _lib.check(rc, "kdot_sinkhorn_fwd_bwd_host")
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    barrier()
+    h2d, d2h = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    L.kdot_host_ctx_last_traffic(ctx, ctypes.byref(h2d), ctypes.byref(d2h))
+    n_valid = int((valid == 1).sum())
+    mean_loss = float(loss.sum() / max(n_valid, 1))
+    L.kdot_host_ctx_destroy(ctx)
+    return dt, int(h2d.value), int(d2h.value), mean_loss
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="kdot", choices=["kdot", "reference"])
+    ap.add_argument("--workload", default="ape_b64", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the secondary dense-workload roofline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the kdot path has no CPU fallback (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from kd_6d_pose_adlp_b200 import _lib
+
+    L = _lib.lib()
+    peaks, peak_src = measured_peaks()
+    fp32_peak = float(L.kdot_measure_fp32_peak_tflops(local_rank, 2000))
+
+    batch = make_batch(args.workload, rank)
+    nimg = len(batch["pos_per_img"])
+    bench = DeviceBench(batch, dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms, per, launches = bench.timed(args.steps, args.warmup, barrier)
+    clocks = sampler.result()
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    value = nimg * world / (ms_per_step * 1e-3)
+
+    nits = bench.nits.cpu().numpy()
+    flops, exps, byts = algorithmic_work(batch, nits)
+    med_ms = statistics.median(per)
+    roofline = {
+        "bound": "fp32", "kernel": "kdot_small_kernel" if launches == args.steps else "kdot_tiled_kernel",
+        "achieved": flops / (ms_per_step * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": flops / (ms_per_step * 1e-3) / 1e12 / fp32_peak if fp32_peak > 0 else None,
+        "peak_source": "FP32 FMA chain measured live on this GPU (kdot_measure_fp32_peak_tflops)",
+        "traffic": None,
+        "sfu_exp_per_s": exps / (ms_per_step * 1e-3),
+        "hbm": {"achieved": byts / (ms_per_step * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "frac": byts / (ms_per_step * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6552.0), "peak_source": peak_src},
+        "algorithmic_flops_per_step": flops, "algorithmic_bytes_per_step": byts, "median_ms_per_step": med_ms,
+    }
+
+    # end to end through the host-buffer C-ABI call
+    e2e_dt, h2d, d2h, mean_loss = host_e2e(batch, local_rank, args.steps, args.warmup, barrier)
+    e2e_dt = max_over_ranks(e2e_dt)
+    e2e = {"value": nimg * world * args.steps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_dt / args.steps * 1e3, "mean_kd_loss": mean_loss}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "images_per_gpu": nimg,
+                   "l2": "256 MiB buffer written between timed steps (L2 flush), inputs restored outside the events",
+                   "parallelism": f"images sharded over {world} rank(s), no data-path collective", **CFG},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1 and not args.no_dense and args.workload != "dense_b32":
+        # secondary leg: the roofline-relevant dense configuration (BASELINE.json configs[2], variant 3b)
+        db = make_batch("dense_b32", 0, nimg=8)
+        dbench = DeviceBench(db, dev)
+        d_total, d_per, d_launch = dbench.timed(3, 1, lambda: None)
+        d_ms = d_total / 3
+        d_fl, d_ex, d_by = algorithmic_work(db, dbench.nits.cpu().numpy())
+        line["dense"] = {
+            "workload": "dense_b32 (8-image sample)", "value": 8 / (d_ms * 1e-3), "unit": UNIT, "ms_per_step": d_ms,
+            "roofline": {"bound": "fp32", "kernel": "kdot_tiled_kernel", "achieved": d_fl / (d_ms * 1e-3) / 1e12,
+                         "peak": fp32_peak, "unit": "TFLOP/s", "frac": d_fl / (d_ms * 1e-3) / 1e12 / fp32_peak,
+                         "sfu_exp_per_s": d_ex / (d_ms * 1e-3), "traffic": None,
+                         "hbm_gbs": d_by / (d_ms * 1e-3) / 1e9},
+        }
+        del dbench
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, passes, dt, cores = cpu_port_images_per_sec(batch, threads=len(os.sched_getaffinity(0)))
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{passes} passes over the {nimg}-image {args.workload} batch in {dt:.1f} s "
+                                          "(fp32 torch CPU ops + autograd: the reference formulation)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
