@@ -8,7 +8,7 @@
 #include "kdot_common.cuh"
 
 namespace kdot {
-cudaError_t launch_small(const SinkhornParams& prm, cudaStream_t stream);
+cudaError_t launch_small(const SinkhornParams& prm, int max_n, int max_m, cudaStream_t stream);
 cudaError_t launch_tiled(const SinkhornParams& prm, int max_n, int max_m, cudaStream_t stream, size_t smem_limit,
                          bool* too_large);
 size_t tiled_smem_bytes(int max_n, int max_m);
@@ -107,7 +107,7 @@ int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt
   cudaStream_t stream = (cudaStream_t)cuda_stream;
 
   if (small_path(max_n, max_m, B)) {
-    cudaError_t e = launch_small(prm, stream);
+    cudaError_t e = launch_small(prm, max_n, max_m, stream);
     if (e != cudaSuccess) return fail_cuda(e, "kdot_small_kernel");
     count_launches(1);
     return KDOT_OK;

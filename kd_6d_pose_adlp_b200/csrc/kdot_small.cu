@@ -1,68 +1,336 @@
-// Fused OT distillation loss, small-problem kernel (N_i + M_i <= 64 cells per image, D = 2).
+// Fused OT distillation loss, small-problem kernels (N_i + M_i <= 64 cells per image, D = 2).
 //
-// One CTA per image, one warp per OT slot (keypoint).  Lane l owns point l (and l+32 when the image
-// has more than 32 cells) of the concatenated cloud [student cells | teacher cells].  Everything the
-// reference does for one image -- losses/loss_libs.py:8-12 (normalise), :22-50 (per-image split) and
-// geomloss' tensorized Sinkhorn divergence with its backward -- runs in this single launch for the
-// whole mini-batch; the N x M cost matrices live only in registers.
+// One CTA per image, one warp per OT slot (keypoint); warps are independent until the final sum over
+// slots.  Everything the reference does for one image -- losses/loss_libs.py:8-12 (normalise), :22-50
+// (per-image split / transposes) and geomloss' tensorized Sinkhorn divergence with its backward -- runs
+// in this single launch for the whole mini-batch; the N x M cost matrices live only in registers.
 //
 // Every point i carries two potentials: S_i against its own cloud (geomloss a_x / b_y) and C_i against
 // the other cloud (b_x / a_y).  With h^S_j = log w_j + S_j/eps and h^C_j = log w_j + C_j/eps the four
 // softmins of a Sinkhorn round collapse to one rule for every row i:
 //   S_i <- lambda * softmin_{j in own cloud}(h^S_j),   C_i <- lambda * softmin_{j in other cloud}(h^C_j).
+//
+// Fast path (N_i + M_i <= 32, the shipped ape shape): lane = row; the columns sit in shared memory as
+// SoA float4 chunks [student cols padded to 4 | teacher cols padded to 4]; the round body is fully
+// unrolled for the image's chunk count (template CH), evaluates 2 columns per instruction with packed
+// f32x2 math, keeps all soft-min arguments in registers (exact max, one exp2 per pair) and needs one
+// __syncwarp per round.  The eps schedule is computed in float64 with one lane per round.
 #include "kdot_common.cuh"
 
 namespace kdot {
 
 constexpr int kSmallMaxPts = 64;
+constexpr int kFastMaxCols = 40;  // padded columns of the fast path (<= 32 points + padding)
+constexpr int kFastMaxCH = kFastMaxCols / 4;
 
-struct RowAcc {
-  float lse_x, lse_y;          // log2-sum-exp over the student / teacher columns
-  float gxx, gxy, sx;          // sum e*(p_j - p_i) and sum e over the student columns   (grad rounds only)
-  float gyx, gyy, sy;          // same over the teacher columns
+// =========================================================================================================
+// fast path
+// =========================================================================================================
+template <int CH, bool GRAD>
+struct RoundOut {
+  float lseX, lseY;        // log2-sum-exp over the student / teacher columns
+  float gXx, gXy, sX;      // sum e * (p_j - p_i) over the student columns and sum e   (GRAD only)
+  float gYx, gYy, sY;
 };
 
-// Two-pass (exact max) log2-sum-exp of row (px,py) against all P columns; the first N columns are the
-// student cloud.  hx / hy select which of (hS,hC) applies to student / teacher columns for this row.
+template <int CH, bool GRAD>
+__device__ __forceinline__ RoundOut<CH, GRAD> fast_round(const float* __restrict__ cx, const float* __restrict__ cy,
+                                                         const float* __restrict__ hp, int nchx, float px, float py,
+                                                         float coef) {
+  const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py), coef2 = make_float2(coef, coef);
+  float2 v[2 * CH];
+  float mX = kNegBig, mY = kNegBig;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const float4 X = reinterpret_cast<const float4*>(cx)[c];
+    const float4 Y = reinterpret_cast<const float4*>(cy)[c];
+    const float4 H = reinterpret_cast<const float4*>(hp)[c];
+    const float2 d0 = __fadd2_rn(make_float2(X.x, X.y), npx), d1 = __fadd2_rn(make_float2(X.z, X.w), npx);
+    const float2 e0 = __fadd2_rn(make_float2(Y.x, Y.y), npy), e1 = __fadd2_rn(make_float2(Y.z, Y.w), npy);
+    v[2 * c] = __ffma2_rn(__ffma2_rn(e0, e0, __fmul2_rn(d0, d0)), coef2, make_float2(H.x, H.y));
+    v[2 * c + 1] = __ffma2_rn(__ffma2_rn(e1, e1, __fmul2_rn(d1, d1)), coef2, make_float2(H.z, H.w));
+    const float m4 = fmaxf(fmaxf(v[2 * c].x, v[2 * c].y), fmaxf(v[2 * c + 1].x, v[2 * c + 1].y));
+    if (c < nchx) mX = fmaxf(mX, m4); else mY = fmaxf(mY, m4);  // warp-uniform
+  }
+  float2 sX = make_float2(0.f, 0.f), sY = sX, gXx = sX, gXy = sX, gYx = sX, gYy = sX;
+  const float2 nmX = make_float2(-mX, -mX), nmY = make_float2(-mY, -mY);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const bool isx = c < nchx;  // warp-uniform
+    const float2 nm = isx ? nmX : nmY;
+    const float2 a0 = __fadd2_rn(v[2 * c], nm), a1 = __fadd2_rn(v[2 * c + 1], nm);
+    const float2 p0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
+    const float2 p1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+    const float2 ps = __fadd2_rn(p0, p1);
+    if (isx) sX = __fadd2_rn(sX, ps); else sY = __fadd2_rn(sY, ps);
+    if (GRAD) {
+      const float4 X = reinterpret_cast<const float4*>(cx)[c];
+      const float4 Y = reinterpret_cast<const float4*>(cy)[c];
+      const float2 d0 = __fadd2_rn(make_float2(X.x, X.y), npx), d1 = __fadd2_rn(make_float2(X.z, X.w), npx);
+      const float2 e0 = __fadd2_rn(make_float2(Y.x, Y.y), npy), e1 = __fadd2_rn(make_float2(Y.z, Y.w), npy);
+      const float2 gx = __ffma2_rn(p1, d1, __fmul2_rn(p0, d0)), gy = __ffma2_rn(p1, e1, __fmul2_rn(p0, e0));
+      if (isx) { gXx = __fadd2_rn(gXx, gx); gXy = __fadd2_rn(gXy, gy); }
+      else     { gYx = __fadd2_rn(gYx, gx); gYy = __fadd2_rn(gYy, gy); }
+    }
+  }
+  RoundOut<CH, GRAD> o;
+  o.sX = sX.x + sX.y; o.sY = sY.x + sY.y;
+  o.lseX = mX + log2f(o.sX);
+  o.lseY = mY + log2f(o.sY);
+  o.gXx = gXx.x + gXx.y; o.gXy = gXy.x + gXy.y;
+  o.gYx = gYx.x + gYx.y; o.gYy = gYy.x + gYy.y;
+  return o;
+}
+
+struct FastCtx {
+  float* cx; float* cy; float* hb;  // per-warp smem: cx[40], cy[40], hb[2 buffers][2 views][40]
+  int nchx;                         // student chunks (padded student columns / 4)
+  bool act, isx;
+  int col;                          // padded column slot of this lane's point
+  float px, py, wgt, lw2;
+};
+
+// All rounds of one (image, slot) for a compile-time chunk count.  Returns via references the final
+// potentials' outputs.  `rc_lane` holds the constants of round (lane) -- broadcast with shuffles.
+template <int CH>
+__device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, int nits, double diam, const SinkhornParams& prm,
+                                           double sched_start, double sched_delta, float& S_out, float& C_out,
+                                           float& gSx, float& gSy, float& gCx, float& gCy, RoundConst& rc_last) {
+  const int lane = threadIdx.x & 31;
+  float potS = 0.f, potC = 0.f;
+  int cur = 0;
+  RoundConst mine = make_round_const(lane, nits, diam, prm.p, prm.blur, sched_start, sched_delta, prm.rho);
+  for (int r = 0; r < nrounds - 1; ++r) {
+    if (r >= 32 && (r & 31) == 0)  // schedules longer than 32 rounds: next block of constants
+      mine = make_round_const(r + lane, nits, diam, prm.p, prm.blur, sched_start, sched_delta, prm.rho);
+    const float coef = __shfl_sync(0xffffffffu, mine.coef, r & 31);
+    const float scale = __shfl_sync(0xffffffffu, mine.scale, r & 31);
+    const float hmul = __shfl_sync(0xffffffffu, mine.hmul, r & 31);
+    const float* hp = c.hb + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
+    const RoundOut<CH, false> o = fast_round<CH, false>(c.cx, c.cy, hp, c.nchx, c.px, c.py, coef);
+    const float nS = scale * (c.isx ? o.lseX : o.lseY);
+    const float nC = scale * (c.isx ? o.lseY : o.lseX);
+    potS = r == 0 ? nS : 0.5f * (potS + nS);
+    potC = r == 0 ? nC : 0.5f * (potC + nC);
+    if (c.act) {
+      float* hn = c.hb + (cur ^ 1) * (2 * kFastMaxCols);
+      const float hS = fmaf(potS, hmul, c.lw2), hC = fmaf(potC, hmul, c.lw2);
+      hn[c.col] = c.isx ? hS : hC;                   // view 0: what student rows read for this column
+      hn[kFastMaxCols + c.col] = c.isx ? hC : hS;    // view 1: what teacher rows read
+    }
+    __syncwarp();
+    cur ^= 1;
+  }
+  const int r = nrounds - 1;
+  if (r >= 32 && (r & 31) == 0)
+    mine = make_round_const(r + lane, nits, diam, prm.p, prm.blur, sched_start, sched_delta, prm.rho);
+  rc_last.coef = __shfl_sync(0xffffffffu, mine.coef, r & 31);
+  rc_last.scale = __shfl_sync(0xffffffffu, mine.scale, r & 31);
+  rc_last.hmul = 0.f;
+  rc_last.eps = __shfl_sync(0xffffffffu, mine.eps, r & 31);
+  const float* hp = c.hb + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
+  const RoundOut<CH, true> o = fast_round<CH, true>(c.cx, c.cy, hp, c.nchx, c.px, c.py, rc_last.coef);
+  S_out = rc_last.scale * (c.isx ? o.lseX : o.lseY);
+  C_out = rc_last.scale * (c.isx ? o.lseY : o.lseX);
+  // barycentric displacements  sum_j W_ij (p_j - p_i)  against own / other cloud (student rows use them)
+  gSx = o.gXx / o.sX; gSy = o.gXy / o.sX;
+  gCx = o.gYx / o.sY; gCy = o.gYy / o.sY;
+}
+
+__global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm) {
+  const int img = blockIdx.x;
+  const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int B = prm.B;
+  extern __shared__ __align__(16) float s_dynf[];  // per warp: cx[40] | cy[40] | h[2][2][40]
+  __shared__ double s_slot_loss[16];
+  float* wbase_s = s_dynf + (size_t)slot * (6 * kFastMaxCols);
+
+  const int n0 = prm.cu_n[img], N = prm.cu_n[img + 1] - n0;
+  const int m0 = prm.cu_m[img], M = prm.cu_m[img + 1] - m0;
+  const int P = N + M;
+  const int Nq = (N + 3) & ~3, Mq = (M + 3) & ~3;
+
+  FastCtx c;
+  c.cx = wbase_s; c.cy = wbase_s + kFastMaxCols; c.hb = wbase_s + 2 * kFastMaxCols;
+  c.nchx = Nq >> 2;
+  c.act = lane < P;
+  c.isx = lane < N;
+  c.col = c.isx ? lane : Nq + (lane - N);
+  c.px = c.py = 0.f; c.wgt = 0.f; c.lw2 = 0.f;
+
+  // ---- image-wide bounding box over all B slots (every warp redundantly: no block barrier needed).  Division by a
+  //      positive constant is monotone, so the box of the normalised points is the normalised box of the raw ones. ----
+  float minx = 3.0e38f, miny = 3.0e38f, maxx = -3.0e38f, maxy = -3.0e38f;
+  long long gidx = 0;
+  float* base = nullptr;
+  if (c.act) {
+    long long cell;
+    long long s_cell, s_slot;
+    const float* wsrc;
+    if (c.isx) { base = prm.xs; cell = n0 + lane; s_cell = prm.s_cell_n; s_slot = prm.s_slot_n; wsrc = prm.ws; }
+    else       { base = prm.xt; cell = m0 + lane - N; s_cell = prm.s_cell_m; s_slot = prm.s_slot_m; wsrc = prm.wt; }
+    for (int s = 0; s < B; ++s) {
+      const float2 v = *reinterpret_cast<const float2*>(base + 2 * (cell * s_cell + (long long)s * s_slot));
+      minx = fminf(minx, v.x); maxx = fmaxf(maxx, v.x);
+      miny = fminf(miny, v.y); maxy = fmaxf(maxy, v.y);
+      if (s == slot) { c.px = v.x; c.py = v.y; }
+    }
+    gidx = cell * s_cell + (long long)slot * s_slot;
+    c.wgt = wsrc ? wsrc[gidx] : __fdiv_rn(1.0f, (float)(c.isx ? N : M));
+    c.lw2 = (c.wgt > 0.f ? logf(c.wgt) : kLogZeroWeight) * kLog2e;
+  }
+  float* gx_out = prm.grad_xs + 2 * gidx;
+  if (prm.normalize) {
+    __syncthreads();  // every warp has read the RAW points of all slots before any slot is overwritten in place
+    if (c.act) {
+      c.px = __fdiv_rn(c.px, prm.w);
+      c.py = __fdiv_rn(c.py, prm.h);
+      *reinterpret_cast<float2*>(base + 2 * gidx) = make_float2(c.px, c.py);
+    }
+  }
+
+  if (N == 0 || M == 0) {  // skipped image (loss_libs.py:25-28); uniform over the CTA
+    if (c.act && c.isx) {
+      *reinterpret_cast<float2*>(gx_out) = make_float2(0.f, 0.f);
+      if (prm.grad_ws) prm.grad_ws[gidx] = 0.f;
+    }
+    if (lane == 0 && prm.loss_per_slot) prm.loss_per_slot[(size_t)img * B + slot] = 0.f;
+    if (threadIdx.x == 0) {
+      prm.loss_per_img[img] = 0.f;
+      prm.valid[img] = KDOT_IMG_SKIPPED;
+      if (prm.nits_per_img) prm.nits_per_img[img] = 0;
+    }
+    return;
+  }
+  minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
+  if (prm.normalize) {
+    minx = __fdiv_rn(minx, prm.w); maxx = __fdiv_rn(maxx, prm.w);
+    miny = __fdiv_rn(miny, prm.h); maxy = __fdiv_rn(maxy, prm.h);
+  }
+  const float diam_f = bbox_diameter(minx, miny, maxx, maxy);
+  int status = KDOT_IMG_OK, nits = 0, nrounds = 0;
+  double sched_start = 0.0, sched_delta = 0.0;
+  if (!(diam_f > 0.f) || !isfinite(diam_f)) {
+    status = KDOT_IMG_DEGENERATE;
+  } else {
+    nits = schedule_len((double)diam_f, prm.p, prm.blur, prm.scaling, &sched_start, &sched_delta);
+    nrounds = nits + 2;
+    if (nrounds > KDOT_MAX_ROUNDS) status = KDOT_IMG_TOO_MANY_ROUNDS;
+  }
+  if (status != KDOT_IMG_OK) {  // uniform over the CTA
+    const float nan = __int_as_float(0x7fc00000);
+    if (c.act && c.isx) {
+      *reinterpret_cast<float2*>(gx_out) = make_float2(nan, nan);
+      if (prm.grad_ws) prm.grad_ws[gidx] = nan;
+    }
+    if (lane == 0 && prm.loss_per_slot) prm.loss_per_slot[(size_t)img * B + slot] = nan;
+    if (threadIdx.x == 0) {
+      prm.loss_per_img[img] = nan;
+      prm.valid[img] = status;
+      if (prm.nits_per_img) prm.nits_per_img[img] = nits;
+    }
+    return;
+  }
+
+  // ---- stage this slot's columns: [student | pad | teacher | pad], pads carry h = -big (exp2 -> 0) ----
+  for (int j = lane; j < kFastMaxCols; j += 32) {
+    c.cx[j] = 0.f; c.cy[j] = 0.f;
+    c.hb[j] = kNegBig; c.hb[kFastMaxCols + j] = kNegBig;
+    c.hb[2 * kFastMaxCols + j] = kNegBig; c.hb[3 * kFastMaxCols + j] = kNegBig;
+  }
+  __syncwarp();
+  if (c.act) {
+    c.cx[c.col] = c.px; c.cy[c.col] = c.py;
+    c.hb[c.col] = c.lw2; c.hb[kFastMaxCols + c.col] = c.lw2;  // init round: h = log w for both views
+  }
+  __syncwarp();
+
+  float S = 0.f, C = 0.f, gSx = 0.f, gSy = 0.f, gCx = 0.f, gCy = 0.f;
+  RoundConst rc;
+  const int ch = (Nq + Mq) >> 2;
+  switch (ch) {
+#define KDOT_CASE(K) case K: fast_solve<K>(c, nrounds, nits, (double)diam_f, prm, sched_start, sched_delta, S, C, gSx, gSy, gCx, gCy, rc); break;
+    KDOT_CASE(2) KDOT_CASE(3) KDOT_CASE(4) KDOT_CASE(5) KDOT_CASE(6) KDOT_CASE(7) KDOT_CASE(8) KDOT_CASE(9)
+    default: fast_solve<kFastMaxCH>(c, nrounds, nits, (double)diam_f, prm, sched_start, sched_delta, S, C, gSx, gSy, gCx, gCy, rc); break;
+#undef KDOT_CASE
+  }
+
+  // ---- loss + analytic backward ----
+  const double rho = prm.rho;
+  const float lam = rho < 0.0 ? 1.f : (float)(1.0 / (1.0 + (double)rc.eps / rho));
+  const float gfac = rho < 0.0 ? 1.f : (float)((rho + 0.5 * (double)rc.eps) / rho) * lam;
+  double loss = 0.0;
+  if (c.act) {
+    const RowFinal f = row_final(S, C, rho, rc.eps);
+    loss = (double)c.wgt * (double)f.term;
+    if (c.isx) {
+      float gx = c.wgt * gfac * (f.eS * gSx - f.eC * gCx);
+      float gy = c.wgt * gfac * (f.eS * gSy - f.eC * gCy);
+      if (prm.normalize) {
+        gx = __fdiv_rn(gx, prm.w);
+        gy = __fdiv_rn(gy, prm.h);
+      }
+      *reinterpret_cast<float2*>(gx_out) = make_float2(gx, gy);
+      if (prm.grad_ws) prm.grad_ws[gidx] = f.term;
+    }
+  }
+  loss = warp_sum(loss);
+  if (lane == 0) {
+    s_slot_loss[slot] = loss;
+    if (prm.loss_per_slot) prm.loss_per_slot[(size_t)img * B + slot] = (float)loss;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int s = 0; s < B; ++s) tot += s_slot_loss[s];
+    prm.loss_per_img[img] = (float)tot;
+    prm.valid[img] = KDOT_IMG_OK;
+    if (prm.nits_per_img) prm.nits_per_img[img] = nits;
+  }
+}
+
+// =========================================================================================================
+// general small path (33..64 points per image): two rows per lane, two-pass exact max
+// =========================================================================================================
+struct RowAcc {
+  float lse_x, lse_y;
+  float gxx, gxy, sx;
+  float gyx, gyy, sy;
+};
+
 template <bool kGrad>
 __device__ __forceinline__ RowAcc row_pass(const float2* __restrict__ pts, const float2* __restrict__ hb, int N, int P,
                                            float px, float py, bool row_is_x, float coef) {
   float mx = kNegBig, my = kNegBig;
+#pragma unroll 4
   for (int j = 0; j < N; ++j) {
     const float2 q = pts[j], hh = hb[j];
     const float dx = q.x - px, dy = q.y - py;
-    const float c = fmaf(dy, dy, dx * dx);
-    mx = fmaxf(mx, fmaf(c, coef, row_is_x ? hh.x : hh.y));
+    mx = fmaxf(mx, fmaf(fmaf(dy, dy, dx * dx), coef, row_is_x ? hh.x : hh.y));
   }
+#pragma unroll 4
   for (int j = N; j < P; ++j) {
     const float2 q = pts[j], hh = hb[j];
     const float dx = q.x - px, dy = q.y - py;
-    const float c = fmaf(dy, dy, dx * dx);
-    my = fmaxf(my, fmaf(c, coef, row_is_x ? hh.y : hh.x));
+    my = fmaxf(my, fmaf(fmaf(dy, dy, dx * dx), coef, row_is_x ? hh.y : hh.x));
   }
   RowAcc a;
   float sx = 0.f, sy = 0.f, gxx = 0.f, gxy = 0.f, gyx = 0.f, gyy = 0.f;
+#pragma unroll 4
   for (int j = 0; j < N; ++j) {
     const float2 q = pts[j], hh = hb[j];
     const float dx = q.x - px, dy = q.y - py;
-    const float c = fmaf(dy, dy, dx * dx);
-    const float e = ex2_approx(fmaf(c, coef, row_is_x ? hh.x : hh.y) - mx);
+    const float e = ex2_approx(fmaf(fmaf(dy, dy, dx * dx), coef, row_is_x ? hh.x : hh.y) - mx);
     sx += e;
-    if (kGrad) {
-      gxx = fmaf(e, dx, gxx);
-      gxy = fmaf(e, dy, gxy);
-    }
+    if (kGrad) { gxx = fmaf(e, dx, gxx); gxy = fmaf(e, dy, gxy); }
   }
+#pragma unroll 4
   for (int j = N; j < P; ++j) {
     const float2 q = pts[j], hh = hb[j];
     const float dx = q.x - px, dy = q.y - py;
-    const float c = fmaf(dy, dy, dx * dx);
-    const float e = ex2_approx(fmaf(c, coef, row_is_x ? hh.y : hh.x) - my);
+    const float e = ex2_approx(fmaf(fmaf(dy, dy, dx * dx), coef, row_is_x ? hh.y : hh.x) - my);
     sy += e;
-    if (kGrad) {
-      gyx = fmaf(e, dx, gyx);
-      gyy = fmaf(e, dy, gyy);
-    }
+    if (kGrad) { gyx = fmaf(e, dx, gyx); gyy = fmaf(e, dy, gyy); }
   }
   a.lse_x = mx + log2f(sx);
   a.lse_y = my + log2f(sy);
@@ -88,10 +356,9 @@ __global__ void __launch_bounds__(512) kdot_small_kernel(SinkhornParams prm) {
   const int P = N + M;
   const bool two = P > 32;
 
-  // ---- load, normalise in place, log-weights ------------------------------------------------------------
   float px[2], py[2], wgt[2], lw2[2];
   bool act[2], isx[2];
-  long long gidx[2];  // element index of this (cell, slot) in xs/ws (student) or xt/wt (teacher)
+  long long gidx[2];
   float minx = 3.0e38f, miny = 3.0e38f, maxx = -3.0e38f, maxy = -3.0e38f;
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
@@ -131,7 +398,7 @@ __global__ void __launch_bounds__(512) kdot_small_kernel(SinkhornParams prm) {
     }
   }
 
-  if (N == 0 || M == 0) {  // skipped image (loss_libs.py:25-28); uniform over the CTA
+  if (N == 0 || M == 0) {  // skipped image; uniform over the CTA
 #pragma unroll
     for (int k = 0; k < 2; ++k)
       if (act[k] && isx[k]) {
@@ -147,7 +414,6 @@ __global__ void __launch_bounds__(512) kdot_small_kernel(SinkhornParams prm) {
     return;
   }
 
-  // ---- image-wide bounding box -> diameter -> eps schedule (float64, as numpy does) ---------------------
   minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
   if (lane == 0) {
     s_box[slot][0] = minx; s_box[slot][1] = miny; s_box[slot][2] = maxx; s_box[slot][3] = maxy;
@@ -189,9 +455,8 @@ __global__ void __launch_bounds__(512) kdot_small_kernel(SinkhornParams prm) {
     }
     return;
   }
-  __syncthreads();  // schedule visible (also orders the pts/hbuf writes of this warp)
+  __syncthreads();
 
-  // ---- Sinkhorn rounds ------------------------------------------------------------------------------------
   float potS[2] = {0.f, 0.f}, potC[2] = {0.f, 0.f};
   int cur = 0;
   for (int r = 0; r < nrounds - 1; ++r) {
@@ -219,7 +484,6 @@ __global__ void __launch_bounds__(512) kdot_small_kernel(SinkhornParams prm) {
     cur ^= 1;
   }
 
-  // ---- last extrapolation (all four potentials from the same old ones) + loss + analytic backward ---------
   const RoundConst rc = s_rc[nrounds - 1];
   const float2* hb = hbuf + cur * kSmallMaxPts;
   const double rho = prm.rho;
@@ -236,7 +500,6 @@ __global__ void __launch_bounds__(512) kdot_small_kernel(SinkhornParams prm) {
       const RowFinal f = row_final(S, C, rho, rc.eps);
       loss += (double)wgt[k] * (double)f.term;
       if (isx[k]) {
-        // own cloud = student columns (gx*, sx), other cloud = teacher columns (gy*, sy)
         float gx = wgt[k] * gfac * (f.eS * (a.gxx / a.sx) - f.eC * (a.gyx / a.sy));
         float gy = wgt[k] * gfac * (f.eS * (a.gxy / a.sx) - f.eC * (a.gyy / a.sy));
         if (prm.normalize) {
@@ -263,9 +526,14 @@ __global__ void __launch_bounds__(512) kdot_small_kernel(SinkhornParams prm) {
   }
 }
 
-cudaError_t launch_small(const SinkhornParams& prm, cudaStream_t stream) {
-  const size_t smem = (size_t)prm.B * 3 * kSmallMaxPts * sizeof(float2);
-  kdot_small_kernel<<<prm.nimg, 32 * prm.B, smem, stream>>>(prm);
+cudaError_t launch_small(const SinkhornParams& prm, int max_n, int max_m, cudaStream_t stream) {
+  if (max_n + max_m <= 32) {
+    const size_t smem = (size_t)prm.B * 6 * kFastMaxCols * sizeof(float);
+    kdot_small_fast_kernel<<<prm.nimg, 32 * prm.B, smem, stream>>>(prm);
+  } else {
+    const size_t smem = (size_t)prm.B * 3 * kSmallMaxPts * sizeof(float2);
+    kdot_small_kernel<<<prm.nimg, 32 * prm.B, smem, stream>>>(prm);
+  }
   return cudaGetLastError();
 }
 

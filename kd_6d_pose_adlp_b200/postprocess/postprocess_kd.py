@@ -1,0 +1,146 @@
+"""``PostProcessorKD`` -- drop-in for ``/root/reference/postprocess/postprocess_kd.py:12`` (teacher knowledge
+extraction: segmentation-weighted cell voting).
+
+Same constructor, same ``forward(box_cls, box_regression, targets, anchors) -> [scores, R, T, det2d]`` (per-image
+lists; ``scores (n,8)`` = sqrt of the seg probability of the selected cells broadcast to the 8 key-points,
+``det2d (n,8,2)`` their key-points un-cropped to full-image pixels; empty ``(0,8)`` / ``(0,8,2)`` tensors when
+nothing is selected or PnP fails -- ``postprocess_kd.py:86-96``).
+
+The reference walks images x levels x labels in Python with a host sync at every ``len()`` / ``min()`` /
+``topk(k=tensor)``; here the whole selection (threshold, per-level arg-max, running-best box size, per-level
+budget ``nk``, per-level top-k, decode) for every (image, class) is ONE kernel launch
+(``kdot_select_cells``) followed by ONE device->host copy of the few selected cells.  RANSAC-EPnP stays
+``cv2.solvePnPRansac`` on the host exactly as in the reference (``postprocess_kd.py:191``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _lib
+
+
+def select_cells(box_cls, box_regression, anchor_sizes, anchor_strides, inference_th, positive_num,
+                 positive_lambda):
+    """Runs the selection kernel.  ``box_cls[l] (nimg, C, H, W)``, ``box_regression[l] (nimg, C*16, H, W)`` CUDA
+    fp32.  Returns a dict of device tensors indexed by ``q = img * C + cls`` (see ``include/kdot.h``)."""
+    L = _lib.lib()
+    nlvl = len(box_cls)
+    nimg, ncls = box_cls[0].shape[0], box_cls[0].shape[1]
+    dev = box_cls[0].device
+    cls_c, reg_c = [], []
+    for c, r in zip(box_cls, box_regression):
+        if not (c.is_cuda and r.is_cuda and c.dtype == torch.float32 and r.dtype == torch.float32):
+            raise ValueError("head outputs must be float32 CUDA tensors (libkdot has no CPU fallback)")
+        if r.shape[1] != ncls * 16 or c.shape[1] != ncls or c.shape[2:] != r.shape[2:]:
+            raise ValueError("inconsistent head output shapes")
+        cls_c.append(c.contiguous())
+        reg_c.append(r.contiguous())
+    nsizes = len(anchor_sizes)
+    cap = int(positive_num) + nsizes + 1
+    nq = nimg * ncls
+    i32 = dict(dtype=torch.int32, device=dev)
+    out = dict(
+        sel_count=torch.empty(nq, **i32), sel_level=torch.empty(nq, cap, **i32), sel_loc=torch.empty(nq, cap, **i32),
+        sel_score=torch.empty(nq, cap, dtype=torch.float32, device=dev),
+        sel_kpts=torch.empty(nq, cap, 16, dtype=torch.float32, device=dev),
+        nk=torch.empty(nq, nsizes, **i32), valid_cnt=torch.empty(nq, nlvl, **i32), best=torch.empty(nq, 2, **i32))
+    ptrs = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    hw = (C.c_int32 * nlvl)(*[int(c.shape[2] * c.shape[3]) for c in cls_c])
+    wd = (C.c_int32 * nlvl)(*[int(c.shape[3]) for c in cls_c])
+    st = (C.c_float * nlvl)(*[float(s) for s in anchor_strides[:nlvl]])
+    sz = (C.c_float * nsizes)(*[float(s) for s in anchor_sizes])
+    with torch.cuda.device(dev):
+        rc = L.kdot_select_cells(ptrs(cls_c), ptrs(reg_c), hw, wd, st, nlvl, sz, nsizes, nimg, ncls,
+                                 float(inference_th), int(positive_num), float(positive_lambda), cap,
+                                 out["sel_count"].data_ptr(), out["sel_level"].data_ptr(), out["sel_loc"].data_ptr(),
+                                 out["sel_score"].data_ptr(), out["sel_kpts"].data_ptr(), out["nk"].data_ptr(),
+                                 out["valid_cnt"].data_ptr(), out["best"].data_ptr(),
+                                 torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "kdot_select_cells")
+    out["cap"], out["ncls"], out["nimg"] = cap, ncls, nimg
+    return out
+
+
+class PostProcessorKD(nn.Module):
+    def __init__(self, inference_th, box_coder, positive_num, positive_lambda, sym_types, symmetry_fn=None):
+        super().__init__()
+        self.inference_th = inference_th
+        self.positive_num = positive_num
+        self.positive_lambda = positive_lambda
+        self.box_coder = box_coder
+        self.sym_types = sym_types
+        self.symmetry_fn = symmetry_fn  # libs.utils.pose_symmetry_handling of the host repo (R only; unused by KD)
+        self.last_selection = None
+
+    def forward(self, box_cls, box_regression, targets, anchors=None):
+        import cv2
+
+        sel = select_cells(box_cls, box_regression, self.box_coder.anchor_sizes, self.box_coder.anchor_strides,
+                           self.inference_th, self.positive_num, self.positive_lambda)
+        dev = box_cls[0].device
+        nimg, ncls, cap = sel["nimg"], sel["ncls"], sel["cap"]
+        # one device->host copy for everything the host part needs
+        count = sel["sel_count"].cpu().numpy().reshape(nimg, ncls)
+        valid = sel["valid_cnt"].cpu().numpy().reshape(nimg, ncls, -1)
+        score = sel["sel_score"].cpu().numpy().reshape(nimg, ncls, cap)
+        kpts = sel["sel_kpts"].cpu().numpy().reshape(nimg, ncls, cap, 16)
+        self.last_selection = dict(count=count, valid=valid, score=score, kpts=kpts,
+                                   level=sel["sel_level"].cpu().numpy().reshape(nimg, ncls, cap),
+                                   loc=sel["sel_loc"].cpu().numpy().reshape(nimg, ncls, cap),
+                                   nk=sel["nk"].cpu().numpy().reshape(nimg, ncls, -1),
+                                   best=sel["best"].cpu().numpy().reshape(nimg, ncls, 2))
+        results = [[], [], [], []]
+        for i in range(nimg):
+            picked = None
+            tgt = targets[i]
+            K_np = tgt.K.detach().cpu().numpy()
+            for c in range(ncls):  # candidate labels in ascending order (torch.unique), first success wins
+                if valid[i, c].sum() == 0 or count[i, c] == 0:
+                    continue
+                n = int(count[i, c])
+                sc = torch.from_numpy(np.broadcast_to(score[i, c, :n, None], (n, 8)).copy())
+                xy2d = torch.from_numpy(kpts[i, c, :n].copy()).view(n, 2, 8).transpose(1, 2).contiguous()  # (n,8,2)
+                if tgt.bbox_trans is not None:
+                    bt = tgt.bbox_trans.detach().cpu().to(torch.float32).view(1, 2, 3).repeat(n, 1, 1)
+                    lin, off = bt[:, :, :2], bt[:, :, 2].unsqueeze(-1)
+                    xy2d = torch.bmm(torch.inverse(lin), xy2d.transpose(1, 2).contiguous() - off).transpose(1, 2).contiguous()
+                xy3d_np = tgt.keypoints_3d[c].detach().cpu().repeat(n, 1, 1).view(-1, 3).numpy()
+                ok, rot, trans, _inl = cv2.solvePnPRansac(xy3d_np, xy2d.view(-1, 2).numpy(), K_np, None,
+                                                          flags=cv2.SOLVEPNP_EPNP, reprojectionError=5.0)
+                if not ok:
+                    continue
+                R = cv2.Rodrigues(rot)[0]
+                T = trans.reshape(-1, 1)
+                if np.isnan(R.sum()) or np.isnan(T.sum()):
+                    continue
+                picked = (sc, c, R, T, xy2d)
+                break
+            if picked is not None:
+                sc, c, R, T, xy2d = picked
+                if self.sym_types is not None and len(self.sym_types) > 0 and ("cls_" + str(c)) in self.sym_types:
+                    if self.symmetry_fn is None:
+                        from libs.utils import pose_symmetry_handling  # host repository
+
+                        self.symmetry_fn = pose_symmetry_handling
+                    R = self.symmetry_fn(R, self.sym_types["cls_" + str(c)])
+                results[0].append(sc.to(dev))
+                results[1].append(R)
+                results[2].append(T)
+                results[3].append(xy2d.to(dev))
+            else:
+                results[0].append(torch.zeros([0, 8], device=dev))
+                results[1].append(torch.zeros([0, 3, 3]))
+                results[2].append(torch.zeros([0, 3, 1]))
+                results[3].append(torch.zeros([0, 8, 2], device=dev))
+        return results
+
+
+def teacher_knowledge(post_processor, pred_cls, pred_reg, targets, anchors=None):
+    """The teacher branch of ``PoseModuleKD.forward`` (``models/model_kd.py:83-92``): the dict the loss consumes."""
+    pred = post_processor(pred_cls, pred_reg, targets, anchors)
+    return {"post_kp_2d": torch.cat(pred[3], dim=0), "post_kp_cls": torch.cat(pred[0], dim=0),
+            "post_pos_per_img": [len(p) for p in pred[0]]}
