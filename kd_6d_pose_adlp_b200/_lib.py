@@ -19,7 +19,7 @@ KDOT_MAX_ROUNDS = 1024
 EXPORTS = (
     "kdot_sinkhorn_fwd_bwd", "kdot_workspace_bytes", "kdot_host_ctx_create", "kdot_host_ctx_destroy",
     "kdot_sinkhorn_fwd_bwd_host", "kdot_host_ctx_last_traffic", "kdot_select_cells", "kdot_last_error",
-    "kdot_version", "kdot_launch_count", "kdot_measure_fp32_peak_tflops",
+    "kdot_version", "kdot_launch_count", "kdot_measure_fp32_peak_tflops", "kdot_debug_set_clock_buffer",
 )
 
 _lib = None
@@ -60,6 +60,7 @@ def lib():
     L.kdot_select_cells.argtypes = (
         [vp] * 5 + [i32, vp, i32, i32, i32, f32, i32, f32, i32] + [vp] * 8 + [vp]
     )
+    L.kdot_debug_set_clock_buffer.argtypes = [vp]
     L.kdot_measure_fp32_peak_tflops.restype = C.c_double
     L.kdot_measure_fp32_peak_tflops.argtypes = [i32, i32]
     _lib = L

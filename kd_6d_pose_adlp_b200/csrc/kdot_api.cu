@@ -1,6 +1,7 @@
 // C-ABI entry points of libkdot.so (see include/kdot.h for the contract and the reference citations).
 #include <atomic>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -15,6 +16,7 @@ size_t tiled_smem_bytes(int max_n, int max_m);
 
 static thread_local std::string g_err;
 static std::atomic<unsigned long long> g_launches{0};
+static long long* g_dbg_clk = nullptr;
 
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -62,6 +64,7 @@ extern "C" {
 
 const char* kdot_last_error(void) { return g_err.c_str(); }
 int kdot_version(void) { return KDOT_VERSION; }
+void kdot_debug_set_clock_buffer(void* dev_ptr) { g_dbg_clk = (long long*)dev_ptr; }
 unsigned long long kdot_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 size_t kdot_workspace_bytes(int nimg, int max_n, int max_m, int B, int D) {
@@ -99,11 +102,17 @@ int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt
   } else {  // single image: N == max_n, M == max_m
     prm.s_cell_n = 1; prm.s_slot_n = max_n; prm.s_cell_m = 1; prm.s_slot_m = max_m;
   }
-  prm.p = (double)p; prm.blur = (double)blur; prm.scaling = (double)scaling;
   prm.rho = reach < 0.f ? -1.0 : pow((double)reach, (double)p);
+  prm.sp.p = (double)p;
+  prm.sp.log_blur_p = (double)p * log((double)blur);
+  prm.sp.log_scaling_p = (double)p * log((double)scaling);
+  prm.sp.eps_final = pow((double)blur, (double)p);
+  prm.sp.rho = prm.rho;
+  for (int k = 0; k < KDOT_SCHED_TABLE; ++k) prm.sp.pow_table[k] = exp((double)k * prm.sp.log_scaling_p);
   prm.w = w; prm.h = h; prm.normalize = normalize;
   prm.loss_per_img = loss_per_img; prm.loss_per_slot = loss_per_slot; prm.valid = valid;
   prm.grad_xs = grad_xs; prm.grad_ws = grad_ws; prm.nits_per_img = nits_per_img;
+  prm.dbg_clk = g_dbg_clk;
   cudaStream_t stream = (cudaStream_t)cuda_stream;
 
   if (small_path(max_n, max_m, B)) {

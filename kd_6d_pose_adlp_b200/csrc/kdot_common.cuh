@@ -7,6 +7,7 @@
 
 namespace kdot {
 
+constexpr int KDOT_SCHED_TABLE = 48;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kNegBig = -1.0e30f;  // "minus infinity" that survives (a - b) without NaN
@@ -23,6 +24,16 @@ struct RoundConst {
   float eps;
 };
 
+// data-independent schedule inputs, precomputed in float64 on the host
+struct SchedParams {
+  double p;              // 1 or 2
+  double log_blur_p;     // p * ln(blur)
+  double log_scaling_p;  // p * ln(scaling)
+  double eps_final;      // blur^p
+  double rho;            // reach^p, < 0 -> balanced
+  double pow_table[KDOT_SCHED_TABLE];  // scaling^(p k) = exp(k * p ln scaling), k = 0..KDOT_SCHED_TABLE-1
+};
+
 struct SinkhornParams {
   float* xs;
   const float* ws;
@@ -33,8 +44,8 @@ struct SinkhornParams {
   int nimg, B;
   // element strides (in cells) of a (cell, slot) pair inside xs/ws and xt/wt
   long long s_cell_n, s_slot_n, s_cell_m, s_slot_m;
-  double p, blur, scaling;
-  double rho;  // reach^p, < 0 -> balanced
+  SchedParams sp;
+  double rho;  // reach^p, < 0 -> balanced   (copy of sp.rho)
   float w, h;
   int normalize;
   float* loss_per_img;
@@ -48,7 +59,12 @@ struct SinkhornParams {
   int32_t* sched_rounds; // [nimg] number of rounds (nits + 2) or <0 status
   float* slot_loss;      // [nimg][B]
   unsigned int* done_ctr; // [nimg]
+  long long* dbg_clk;     // optional [nimg][8] SM-clock stamps (kdot_debug_set_clock_buffer), NULL in production
 };
+
+__device__ __forceinline__ void dbg_stamp(const SinkhornParams& p, int img, int k) {
+  if (p.dbg_clk && threadIdx.x == 0) p.dbg_clk[(size_t)img * 8 + k] = clock64();
+}
 
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
@@ -72,29 +88,63 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// log2 on the SFU.  Used only for log2(sum of exps) with the sum in [1, #columns]: the 2^-22 relative error of
+// lg2.approx is far below the fp32 rounding of the running max it is added to (|max| ~ 1e2..1e4).
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // geomloss max_diameter on fp32 data: |maxs - mins|_2 evaluated without FMA contraction.
 __device__ __forceinline__ float bbox_diameter(float minx, float miny, float maxx, float maxy) {
   const float ex = __fsub_rn(maxx, minx), ey = __fsub_rn(maxy, miny);
   return sqrtf(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
 }
 
-// Number of geomloss schedule entries: len([diam^p] + arange(p ln diam, p ln blur, p ln scaling) + [blur^p]).
-__device__ __forceinline__ int schedule_len(double diam, double p, double blur, double scaling, double* start,
-                                            double* delta) {
-  const double a = p * log(diam), b = p * log(blur), s = p * log(scaling);
-  double len = ceil((b - a) / s);
+// ---- geomloss' epsilon schedule -------------------------------------------------------------------------
+//   eps_s = [diam^p] + [exp(e) for e in arange(p ln diam, p ln blur, p ln scaling)] + [blur^p]     (float64)
+// i.e. eps_s[1 + k] = diam^p * scaling^(p k) for every k >= 0 with diam^p * scaling^(p k) > blur^p.
+// The data-independent factors scaling^(p k) (k < KDOT_SCHED_TABLE), p ln blur, p ln scaling and blur^p are
+// precomputed in float64 on the host (SchedParams), so the common case needs no fp64 transcendental on the
+// device: a few DMUL/DSETP per round.  Longer schedules (scaling close to 1) take the log/exp route below.
+// Both routes agree with numpy's arange/exp to a few ulps of float64 (1e-15 relative on eps); the schedule
+// LENGTH can differ only if diam^p * scaling^(p k) hits blur^p to within that error.
+struct ImgSched {
+  int nits;       // len(eps_s)
+  int slow;       // 1: schedule longer than the host table, use start/delta with exp()
+  double start;   // p ln diam                                   (slow route only)
+  double delta;   // numpy arange step (start + step) - start     (slow route only)
+  double eps0;    // diam^p
+};
+
+static __device__ __noinline__ ImgSched image_schedule_slow(double diam, double p, double log_blur_p,
+                                                            double log_scaling_p, double eps0) {
+  ImgSched is;
+  const double a = p * log(diam);
+  double len = ceil((log_blur_p - a) / log_scaling_p);
   if (!(len > 0.0)) len = 0.0;
-  *start = a;
-  *delta = (a + s) - a;  // numpy arange fills with start + i * ((start + step) - start)
-  return (int)len + 2;
+  is.nits = (int)len + 2;
+  is.slow = 1;
+  is.start = a;
+  is.delta = (a + log_scaling_p) - a;
+  is.eps0 = eps0;
+  return is;
 }
 
-// eps of geomloss' eps_s[t], t in [0, nits)
-__device__ __forceinline__ double schedule_eps(int t, int nits, double diam, double p, double blur, double start,
-                                               double delta) {
-  if (t <= 0) return pow(diam, p);
-  if (t >= nits - 1) return pow(blur, p);
-  return exp(start + (double)(t - 1) * delta);
+__device__ __forceinline__ ImgSched image_schedule(float diam_f, const SchedParams& sp) {
+  const double diam = (double)diam_f;
+  const double eps0 = sp.p == 2.0 ? diam * diam : diam;  // p in {1, 2}
+  if (eps0 * sp.pow_table[KDOT_SCHED_TABLE - 1] > sp.eps_final) return image_schedule_slow(diam, sp.p, sp.log_blur_p, sp.log_scaling_p, eps0);
+  ImgSched is;
+  int len = 0;
+  while (len < KDOT_SCHED_TABLE && eps0 * sp.pow_table[len] > sp.eps_final) ++len;
+  is.nits = len + 2;
+  is.slow = 0;
+  is.start = 0.0;
+  is.delta = 0.0;
+  is.eps0 = eps0;
+  return is;
 }
 
 // Round r of the kernel's flattened loop: r = 0 init (eps_s[0]), 1..nits the loop, nits+1 the last extrapolation.
@@ -104,11 +154,21 @@ __device__ __forceinline__ int round_to_sched(int r, int nits) {
   return nits - 1;
 }
 
-__device__ __forceinline__ RoundConst make_round_const(int r, int nits, double diam, double p, double blur,
-                                                       double start, double delta, double rho) {
-  const double eps = schedule_eps(round_to_sched(r, nits), nits, diam, p, blur, start, delta);
-  const double eps_next = schedule_eps(round_to_sched(r + 1, nits), nits, diam, p, blur, start, delta);
-  const double lam = rho < 0.0 ? 1.0 : 1.0 / (1.0 + eps / rho);
+static __device__ __noinline__ double schedule_eps_slow(int k, double start, double delta) {
+  return exp(start + (double)k * delta);
+}
+
+__device__ __forceinline__ double schedule_eps(int t, const ImgSched& is, const SchedParams& sp) {
+  if (t <= 0) return is.eps0;
+  if (t >= is.nits - 1) return sp.eps_final;
+  if (!is.slow) return is.eps0 * sp.pow_table[t - 1];
+  return schedule_eps_slow(t - 1, is.start, is.delta);
+}
+
+__device__ __forceinline__ RoundConst make_round_const(int r, const ImgSched& is, const SchedParams& sp) {
+  const double eps = schedule_eps(round_to_sched(r, is.nits), is, sp);
+  const double eps_next = schedule_eps(round_to_sched(r + 1, is.nits), is, sp);
+  const double lam = sp.rho < 0.0 ? 1.0 : 1.0 / (1.0 + eps / sp.rho);
   RoundConst rc;
   rc.coef = (float)(-0.5 * 1.4426950408889634 / eps);
   rc.scale = (float)(-lam * eps * 0.6931471805599453);

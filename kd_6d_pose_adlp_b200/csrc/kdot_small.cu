@@ -15,7 +15,11 @@
 // unrolled for the image's chunk count (template CH), evaluates 2 columns per instruction with packed
 // f32x2 math, keeps all soft-min arguments in registers (exact max, one exp2 per pair) and needs one
 // __syncwarp per round.  The eps schedule is computed in float64 with one lane per round.
+#include <cooperative_groups.h>
+
 #include "kdot_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace kdot {
 
@@ -75,8 +79,8 @@ __device__ __forceinline__ RoundOut<CH, GRAD> fast_round(const float* __restrict
   }
   RoundOut<CH, GRAD> o;
   o.sX = sX.x + sX.y; o.sY = sY.x + sY.y;
-  o.lseX = mX + log2f(o.sX);
-  o.lseY = mY + log2f(o.sY);
+  o.lseX = mX + lg2_approx(o.sX);
+  o.lseY = mY + lg2_approx(o.sY);
   o.gXx = gXx.x + gXx.y; o.gXy = gXy.x + gXy.y;
   o.gYx = gYx.x + gYx.y; o.gYy = gYy.x + gYy.y;
   return o;
@@ -93,16 +97,15 @@ struct FastCtx {
 // All rounds of one (image, slot) for a compile-time chunk count.  Returns via references the final
 // potentials' outputs.  `rc_lane` holds the constants of round (lane) -- broadcast with shuffles.
 template <int CH>
-__device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, int nits, double diam, const SinkhornParams& prm,
-                                           double sched_start, double sched_delta, float& S_out, float& C_out,
+__device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const ImgSched& is, const SinkhornParams& prm,
+                                           RoundConst mine, float& S_out, float& C_out,
                                            float& gSx, float& gSy, float& gCx, float& gCy, RoundConst& rc_last) {
   const int lane = threadIdx.x & 31;
   float potS = 0.f, potC = 0.f;
   int cur = 0;
-  RoundConst mine = make_round_const(lane, nits, diam, prm.p, prm.blur, sched_start, sched_delta, prm.rho);
   for (int r = 0; r < nrounds - 1; ++r) {
     if (r >= 32 && (r & 31) == 0)  // schedules longer than 32 rounds: next block of constants
-      mine = make_round_const(r + lane, nits, diam, prm.p, prm.blur, sched_start, sched_delta, prm.rho);
+      mine = make_round_const(r + lane, is, prm.sp);
     const float coef = __shfl_sync(0xffffffffu, mine.coef, r & 31);
     const float scale = __shfl_sync(0xffffffffu, mine.scale, r & 31);
     const float hmul = __shfl_sync(0xffffffffu, mine.hmul, r & 31);
@@ -123,7 +126,7 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, int ni
   }
   const int r = nrounds - 1;
   if (r >= 32 && (r & 31) == 0)
-    mine = make_round_const(r + lane, nits, diam, prm.p, prm.blur, sched_start, sched_delta, prm.rho);
+    mine = make_round_const(r + lane, is, prm.sp);
   rc_last.coef = __shfl_sync(0xffffffffu, mine.coef, r & 31);
   rc_last.scale = __shfl_sync(0xffffffffu, mine.scale, r & 31);
   rc_last.hmul = 0.f;
@@ -137,19 +140,33 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, int ni
   gCx = o.gYx / o.sY; gCy = o.gYy / o.sY;
 }
 
-__global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm) {
-  const int img = blockIdx.x;
-  const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// The B slots of an image are spread over a thread-block cluster of `split` CTAs (B/split warps each) so that a
+// small batch still covers the whole chip with about one warp per SM sub-partition: the rounds are bound by the
+// per-sub-partition SFU / FP32 pipes, not by occupancy.  The cluster is only needed twice: a barrier before the
+// in-place normalisation (every CTA reads all slots for the bounding box) and the fixed-order sum over slots,
+// which rank 0 performs on values its peers wrote into its shared memory (DSMEM).
+__global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm, int split) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int img = blockIdx.x / split, part = blockIdx.x - img * split;
+  const int wpc = prm.B / split;  // warps (slots) per CTA
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = part * wpc + warp;
   const int B = prm.B;
   extern __shared__ __align__(16) float s_dynf[];  // per warp: cx[40] | cy[40] | h[2][2][40]
-  __shared__ double s_slot_loss[16];
-  float* wbase_s = s_dynf + (size_t)slot * (6 * kFastMaxCols);
+  __shared__ double s_slot_loss[16];               // rank 0's copy collects all B slots
+  float* wbase_s = s_dynf + (size_t)warp * (6 * kFastMaxCols);
 
   const int n0 = prm.cu_n[img], N = prm.cu_n[img + 1] - n0;
   const int m0 = prm.cu_m[img], M = prm.cu_m[img + 1] - m0;
   const int P = N + M;
   const int Nq = (N + 3) & ~3, Mq = (M + 3) & ~3;
 
+  dbg_stamp(prm, img, 0);
+  if (prm.dbg_clk && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    prm.dbg_clk[(size_t)img * 8 + 7] = (long long)t;
+  }
   FastCtx c;
   c.cx = wbase_s; c.cy = wbase_s + kFastMaxCols; c.hb = wbase_s + 2 * kFastMaxCols;
   c.nchx = Nq >> 2;
@@ -169,19 +186,27 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
     const float* wsrc;
     if (c.isx) { base = prm.xs; cell = n0 + lane; s_cell = prm.s_cell_n; s_slot = prm.s_slot_n; wsrc = prm.ws; }
     else       { base = prm.xt; cell = m0 + lane - N; s_cell = prm.s_cell_m; s_slot = prm.s_slot_m; wsrc = prm.wt; }
-    for (int s = 0; s < B; ++s) {
-      const float2 v = *reinterpret_cast<const float2*>(base + 2 * (cell * s_cell + (long long)s * s_slot));
-      minx = fminf(minx, v.x); maxx = fmaxf(maxx, v.x);
-      miny = fminf(miny, v.y); maxy = fmaxf(maxy, v.y);
-      if (s == slot) { c.px = v.x; c.py = v.y; }
+    for (int s0 = 0; s0 < B; s0 += 8) {  // all loads of a batch of 8 slots in flight together
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = *reinterpret_cast<const float2*>(base + 2 * (cell * s_cell + (long long)min(s0 + u, B - 1) * s_slot));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        minx = fminf(minx, v[u].x); maxx = fmaxf(maxx, v[u].x);
+        miny = fminf(miny, v[u].y); maxy = fmaxf(maxy, v[u].y);
+        if (s0 + u == slot) { c.px = v[u].x; c.py = v[u].y; }
+      }
     }
     gidx = cell * s_cell + (long long)slot * s_slot;
     c.wgt = wsrc ? wsrc[gidx] : __fdiv_rn(1.0f, (float)(c.isx ? N : M));
     c.lw2 = (c.wgt > 0.f ? logf(c.wgt) : kLogZeroWeight) * kLog2e;
   }
   float* gx_out = prm.grad_xs + 2 * gidx;
+  dbg_stamp(prm, img, 1);
   if (prm.normalize) {
-    __syncthreads();  // every warp has read the RAW points of all slots before any slot is overwritten in place
+    // every warp of every CTA of the image has read the RAW points of all slots before any slot is overwritten
+    if (split > 1) cluster.sync(); else __syncthreads();
     if (c.act) {
       c.px = __fdiv_rn(c.px, prm.w);
       c.py = __fdiv_rn(c.py, prm.h);
@@ -195,7 +220,7 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
       if (prm.grad_ws) prm.grad_ws[gidx] = 0.f;
     }
     if (lane == 0 && prm.loss_per_slot) prm.loss_per_slot[(size_t)img * B + slot] = 0.f;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && part == 0) {
       prm.loss_per_img[img] = 0.f;
       prm.valid[img] = KDOT_IMG_SKIPPED;
       if (prm.nits_per_img) prm.nits_per_img[img] = 0;
@@ -208,12 +233,15 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
     miny = __fdiv_rn(miny, prm.h); maxy = __fdiv_rn(maxy, prm.h);
   }
   const float diam_f = bbox_diameter(minx, miny, maxx, maxy);
+  dbg_stamp(prm, img, 2);
   int status = KDOT_IMG_OK, nits = 0, nrounds = 0;
-  double sched_start = 0.0, sched_delta = 0.0;
+  ImgSched is;
+  is.nits = 0; is.start = 0.0; is.delta = 0.0; is.eps0 = 0.0;
   if (!(diam_f > 0.f) || !isfinite(diam_f)) {
     status = KDOT_IMG_DEGENERATE;
   } else {
-    nits = schedule_len((double)diam_f, prm.p, prm.blur, prm.scaling, &sched_start, &sched_delta);
+    is = image_schedule(diam_f, prm.sp);
+    nits = is.nits;
     nrounds = nits + 2;
     if (nrounds > KDOT_MAX_ROUNDS) status = KDOT_IMG_TOO_MANY_ROUNDS;
   }
@@ -224,7 +252,7 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
       if (prm.grad_ws) prm.grad_ws[gidx] = nan;
     }
     if (lane == 0 && prm.loss_per_slot) prm.loss_per_slot[(size_t)img * B + slot] = nan;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && part == 0) {
       prm.loss_per_img[img] = nan;
       prm.valid[img] = status;
       if (prm.nits_per_img) prm.nits_per_img[img] = nits;
@@ -232,6 +260,7 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
     return;
   }
 
+  dbg_stamp(prm, img, 3);
   // ---- stage this slot's columns: [student | pad | teacher | pad], pads carry h = -big (exp2 -> 0) ----
   for (int j = lane; j < kFastMaxCols; j += 32) {
     c.cx[j] = 0.f; c.cy[j] = 0.f;
@@ -247,14 +276,17 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
 
   float S = 0.f, C = 0.f, gSx = 0.f, gSy = 0.f, gCx = 0.f, gCy = 0.f;
   RoundConst rc;
+  const RoundConst mine = make_round_const(lane, is, prm.sp);  // lane r holds the constants of round r
+  dbg_stamp(prm, img, 4);
   const int ch = (Nq + Mq) >> 2;
   switch (ch) {
-#define KDOT_CASE(K) case K: fast_solve<K>(c, nrounds, nits, (double)diam_f, prm, sched_start, sched_delta, S, C, gSx, gSy, gCx, gCy, rc); break;
+#define KDOT_CASE(K) case K: fast_solve<K>(c, nrounds, is, prm, mine, S, C, gSx, gSy, gCx, gCy, rc); break;
     KDOT_CASE(2) KDOT_CASE(3) KDOT_CASE(4) KDOT_CASE(5) KDOT_CASE(6) KDOT_CASE(7) KDOT_CASE(8) KDOT_CASE(9)
-    default: fast_solve<kFastMaxCH>(c, nrounds, nits, (double)diam_f, prm, sched_start, sched_delta, S, C, gSx, gSy, gCx, gCy, rc); break;
+    default: fast_solve<kFastMaxCH>(c, nrounds, is, prm, mine, S, C, gSx, gSy, gCx, gCy, rc); break;
 #undef KDOT_CASE
   }
 
+  dbg_stamp(prm, img, 5);
   // ---- loss + analytic backward ----
   const double rho = prm.rho;
   const float lam = rho < 0.0 ? 1.f : (float)(1.0 / (1.0 + (double)rc.eps / rho));
@@ -276,13 +308,15 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
   }
   loss = warp_sum(loss);
   if (lane == 0) {
-    s_slot_loss[slot] = loss;
+    double* dst = split > 1 ? cluster.map_shared_rank(s_slot_loss, 0) : s_slot_loss;  // rank 0 collects
+    dst[slot] = loss;
     if (prm.loss_per_slot) prm.loss_per_slot[(size_t)img * B + slot] = (float)loss;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  if (split > 1) cluster.sync(); else __syncthreads();
+  if (threadIdx.x == 0 && part == 0) {
     double tot = 0.0;
-    for (int s = 0; s < B; ++s) tot += s_slot_loss[s];
+    for (int s = 0; s < B; ++s) tot += s_slot_loss[s];  // fixed order: deterministic
+    if (prm.dbg_clk) prm.dbg_clk[(size_t)img * 8 + 6] = clock64();
     prm.loss_per_img[img] = (float)tot;
     prm.valid[img] = KDOT_IMG_OK;
     if (prm.nits_per_img) prm.nits_per_img[img] = nits;
@@ -332,8 +366,8 @@ __device__ __forceinline__ RowAcc row_pass(const float2* __restrict__ pts, const
     sy += e;
     if (kGrad) { gyx = fmaf(e, dx, gyx); gyy = fmaf(e, dy, gyy); }
   }
-  a.lse_x = mx + log2f(sx);
-  a.lse_y = my + log2f(sy);
+  a.lse_x = mx + lg2_approx(sx);
+  a.lse_y = my + lg2_approx(sy);
   a.gxx = gxx; a.gxy = gxy; a.sx = sx;
   a.gyx = gyx; a.gyy = gyy; a.sy = sy;
   return a;
@@ -429,14 +463,13 @@ __global__ void __launch_bounds__(512) kdot_small_kernel(SinkhornParams prm) {
   if (!(diam_f > 0.f) || !isfinite(diam_f)) {
     status = KDOT_IMG_DEGENERATE;
   } else {
-    double start, delta;
-    nits = schedule_len((double)diam_f, prm.p, prm.blur, prm.scaling, &start, &delta);
+    const ImgSched is = image_schedule(diam_f, prm.sp);
+    nits = is.nits;
     nrounds = nits + 2;
     if (nrounds > KDOT_MAX_ROUNDS) {
       status = KDOT_IMG_TOO_MANY_ROUNDS;
     } else {
-      for (int r = threadIdx.x; r < nrounds; r += blockDim.x)
-        s_rc[r] = make_round_const(r, nits, (double)diam_f, prm.p, prm.blur, start, delta, prm.rho);
+      for (int r = threadIdx.x; r < nrounds; r += blockDim.x) s_rc[r] = make_round_const(r, is, prm.sp);
     }
   }
   if (status != KDOT_IMG_OK) {  // uniform over the CTA
@@ -528,8 +561,31 @@ __global__ void __launch_bounds__(512) kdot_small_kernel(SinkhornParams prm) {
 
 cudaError_t launch_small(const SinkhornParams& prm, int max_n, int max_m, cudaStream_t stream) {
   if (max_n + max_m <= 32) {
-    const size_t smem = (size_t)prm.B * 6 * kFastMaxCols * sizeof(float);
-    kdot_small_fast_kernel<<<prm.nimg, 32 * prm.B, smem, stream>>>(prm);
+    // spread the slots of an image over a cluster until the grid has about one warp per SM sub-partition
+    static int sm_count = 0;
+    if (sm_count == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+      if (sm_count <= 0) sm_count = 148;
+    }
+    int split = 1;
+    while (split < 8 && prm.B % (split * 2) == 0 && (long long)prm.nimg * split * 2 <= (long long)sm_count) split *= 2;
+    const int wpc = prm.B / split;
+    const size_t smem = (size_t)wpc * 6 * kFastMaxCols * sizeof(float);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(prm.nimg * split);
+    cfg.blockDim = dim3(32 * wpc);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = split;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kdot_small_fast_kernel, prm, split);
   } else {
     const size_t smem = (size_t)prm.B * 3 * kSmallMaxPts * sizeof(float2);
     kdot_small_kernel<<<prm.nimg, 32 * prm.B, smem, stream>>>(prm);

@@ -17,7 +17,7 @@
 namespace kdot {
 
 constexpr int kTiledThreads = 256;
-constexpr int kRows = 2;                     // rows per lane
+constexpr int kRows = 4;                     // rows per lane
 constexpr int kUnitRows = 32 * kRows;        // rows per warp unit
 constexpr float kTau = 24.f;                 // lazy-rescale threshold (log2 units)
 
@@ -33,8 +33,7 @@ __global__ void __launch_bounds__(256) kdot_prep_kernel(SinkhornParams prm) {
   const int m0 = prm.cu_m[img], M = prm.cu_m[img + 1] - m0;
   __shared__ float s_box[8][4];
   __shared__ int s_info[2];
-  __shared__ double s_sched[2];
-  __shared__ float s_diam;
+  __shared__ ImgSched s_is;
 
   float minx = 3.0e38f, miny = 3.0e38f, maxx = -3.0e38f, maxy = -3.0e38f;
   for (int t = threadIdx.x; t < (N + M) * B; t += blockDim.x) {
@@ -76,13 +75,13 @@ __global__ void __launch_bounds__(256) kdot_prep_kernel(SinkhornParams prm) {
       if (!(diam > 0.f) || !isfinite(diam)) {
         status = KDOT_IMG_DEGENERATE;
       } else {
-        nits = schedule_len((double)diam, prm.p, prm.blur, prm.scaling, &s_sched[0], &s_sched[1]);
+        s_is = image_schedule(diam, prm.sp);
+        nits = s_is.nits;
         if (nits + 2 > KDOT_MAX_ROUNDS) status = KDOT_IMG_TOO_MANY_ROUNDS;
       }
     }
     s_info[0] = status;
     s_info[1] = nits;
-    s_diam = diam;
     prm.sched_rounds[img] = status == KDOT_IMG_OK ? nits + 2 : 0;
     prm.done_ctr[img] = 0u;
     prm.valid[img] = status;
@@ -93,8 +92,7 @@ __global__ void __launch_bounds__(256) kdot_prep_kernel(SinkhornParams prm) {
   const int status = s_info[0], nits = s_info[1];
   if (status == KDOT_IMG_OK) {
     for (int r = threadIdx.x; r < nits + 2; r += blockDim.x)
-      prm.sched[(size_t)img * KDOT_MAX_ROUNDS + r] =
-          make_round_const(r, nits, (double)s_diam, prm.p, prm.blur, s_sched[0], s_sched[1], prm.rho);
+      prm.sched[(size_t)img * KDOT_MAX_ROUNDS + r] = make_round_const(r, s_is, prm.sp);
   } else {
     const float fill = status == KDOT_IMG_SKIPPED ? 0.f : __int_as_float(0x7fc00000);
     for (int t = threadIdx.x; t < N * B; t += blockDim.x) {
@@ -115,7 +113,8 @@ template <bool kGrad>
 struct RowState {
   float2 nx, ny;    // (-px, -px), (-py, -py)
   float2 nm;        // (-mref, -mref)
-  float mref;
+  float mref;       // reference exponent of the running sums (stale by at most kTau)
+  float thr;        // mref + kTau: a larger value triggers a re-base
   float2 s;         // two partial exp sums
   float2 gx, gy;    // sum e * (p_j - p_i), two partials each   (kGrad only)
 };
@@ -125,42 +124,55 @@ __device__ __forceinline__ void rows_vs_columns(RowState<kGrad> (&st)[kRows], co
                                                 const float* __restrict__ cy, const float* __restrict__ ch, int c0,
                                                 int c1, float coef) {
   const float2 coef2 = make_float2(coef, coef);
-#pragma unroll 2
+#pragma unroll 1
   for (int j = c0; j < c1; j += 4) {
     const float4 X = *reinterpret_cast<const float4*>(cx + j);
     const float4 Y = *reinterpret_cast<const float4*>(cy + j);
     const float4 H = *reinterpret_cast<const float4*>(ch + j);
+    float2 v0[kRows], v1[kRows], d0[kRows], d1[kRows], e0[kRows], e1[kRows];
+    bool rebase = false;
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {
-      const float2 d0 = __fadd2_rn(make_float2(X.x, X.y), st[k].nx);
-      const float2 d1 = __fadd2_rn(make_float2(X.z, X.w), st[k].nx);
-      const float2 e0 = __fadd2_rn(make_float2(Y.x, Y.y), st[k].ny);
-      const float2 e1 = __fadd2_rn(make_float2(Y.z, Y.w), st[k].ny);
-      const float2 q0 = __ffma2_rn(e0, e0, __fmul2_rn(d0, d0));
-      const float2 q1 = __ffma2_rn(e1, e1, __fmul2_rn(d1, d1));
-      const float2 v0 = __ffma2_rn(q0, coef2, make_float2(H.x, H.y));
-      const float2 v1 = __ffma2_rn(q1, coef2, make_float2(H.z, H.w));
-      const float vm = fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y));
-      if (vm > st[k].mref + kTau) {  // rare after the first chunk: re-base the running sums
-        const float sc = ex2_approx(st[k].mref - vm);
-        st[k].s.x *= sc; st[k].s.y *= sc;
-        if (kGrad) {
-          st[k].gx.x *= sc; st[k].gx.y *= sc;
-          st[k].gy.x *= sc; st[k].gy.y *= sc;
+      d0[k] = __fadd2_rn(make_float2(X.x, X.y), st[k].nx);
+      d1[k] = __fadd2_rn(make_float2(X.z, X.w), st[k].nx);
+      e0[k] = __fadd2_rn(make_float2(Y.x, Y.y), st[k].ny);
+      e1[k] = __fadd2_rn(make_float2(Y.z, Y.w), st[k].ny);
+      const float2 q0 = __ffma2_rn(e0[k], e0[k], __fmul2_rn(d0[k], d0[k]));
+      const float2 q1 = __ffma2_rn(e1[k], e1[k], __fmul2_rn(d1[k], d1[k]));
+      v0[k] = __ffma2_rn(q0, coef2, make_float2(H.x, H.y));
+      v1[k] = __ffma2_rn(q1, coef2, make_float2(H.z, H.w));
+      const float vm = fmaxf(fmaxf(v0[k].x, v0[k].y), fmaxf(v1[k].x, v1[k].y));
+      rebase |= vm > st[k].thr;
+    }
+    if (rebase) {  // cold: some row met a value more than kTau above its reference -> re-base its running sums
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) {
+        const float vm = fmaxf(fmaxf(v0[k].x, v0[k].y), fmaxf(v1[k].x, v1[k].y));
+        if (vm > st[k].thr) {
+          const float sc = ex2_approx(st[k].mref - vm);
+          st[k].s.x *= sc; st[k].s.y *= sc;
+          if (kGrad) {
+            st[k].gx.x *= sc; st[k].gx.y *= sc;
+            st[k].gy.x *= sc; st[k].gy.y *= sc;
+          }
+          st[k].mref = vm;
+          st[k].thr = vm + kTau;
+          st[k].nm = make_float2(-vm, -vm);
         }
-        st[k].mref = vm;
-        st[k].nm = make_float2(-vm, -vm);
       }
-      const float2 a0 = __fadd2_rn(v0, st[k].nm);
-      const float2 a1 = __fadd2_rn(v1, st[k].nm);
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const float2 a0 = __fadd2_rn(v0[k], st[k].nm);
+      const float2 a1 = __fadd2_rn(v1[k], st[k].nm);
       const float2 p0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
       const float2 p1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
       st[k].s = __fadd2_rn(st[k].s, __fadd2_rn(p0, p1));
       if (kGrad) {
-        st[k].gx = __ffma2_rn(p0, d0, st[k].gx);
-        st[k].gx = __ffma2_rn(p1, d1, st[k].gx);
-        st[k].gy = __ffma2_rn(p0, e0, st[k].gy);
-        st[k].gy = __ffma2_rn(p1, e1, st[k].gy);
+        st[k].gx = __ffma2_rn(p0, d0[k], st[k].gx);
+        st[k].gx = __ffma2_rn(p1, d1[k], st[k].gx);
+        st[k].gy = __ffma2_rn(p0, e0[k], st[k].gy);
+        st[k].gy = __ffma2_rn(p1, e1[k], st[k].gy);
       }
     }
   }
@@ -171,6 +183,7 @@ __device__ __forceinline__ void rows_reset(RowState<kGrad> (&st)[kRows]) {
 #pragma unroll
   for (int k = 0; k < kRows; ++k) {
     st[k].mref = kNegBig;
+    st[k].thr = kNegBig;
     st[k].nm = make_float2(-kNegBig, -kNegBig);
     st[k].s = make_float2(0.f, 0.f);
     st[k].gx = make_float2(0.f, 0.f);
@@ -274,7 +287,7 @@ __global__ void __launch_bounds__(kTiledThreads, 2) kdot_tiled_kernel(SinkhornPa
 #pragma unroll
       for (int k = 0; k < kRows; ++k) {
         if (ridx[k] < 0) continue;
-        const float lse = st[k].mref + log2f(st[k].s.x + st[k].s.y);
+        const float lse = st[k].mref + lg2_approx(st[k].s.x + st[k].s.y);
         float* pot = own ? potS : potC;
         const float nv = rc.scale * lse;
         const float pv = r == 0 ? nv : 0.5f * (pot[ridx[k]] + nv);
@@ -321,7 +334,7 @@ __global__ void __launch_bounds__(kTiledThreads, 2) kdot_tiled_kernel(SinkhornPa
 #pragma unroll
         for (int k = 0; k < kRows; ++k) {
           const float s = st[k].s.x + st[k].s.y;
-          S[k] = rc.scale * (st[k].mref + log2f(s));
+          S[k] = rc.scale * (st[k].mref + lg2_approx(s));
           gSx[k] = (st[k].gx.x + st[k].gx.y) / s;
           gSy[k] = (st[k].gy.x + st[k].gy.y) / s;
         }
@@ -331,7 +344,7 @@ __global__ void __launch_bounds__(kTiledThreads, 2) kdot_tiled_kernel(SinkhornPa
         for (int k = 0; k < kRows; ++k) {
           if (ridx[k] < 0) continue;
           const float s = st[k].s.x + st[k].s.y;
-          const float C = rc.scale * (st[k].mref + log2f(s));
+          const float C = rc.scale * (st[k].mref + lg2_approx(s));
           const float gCx = (st[k].gx.x + st[k].gx.y) / s;
           const float gCy = (st[k].gy.x + st[k].gy.y) / s;
           const RowFinal f = row_final(S[k], C, rho, rc.eps);
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(kTiledThreads, 2) kdot_tiled_kernel(SinkhornPa
 #pragma unroll
         for (int k = 0; k < kRows; ++k) {
           if (ridx[k] < 0) continue;
-          (own ? potS : potC)[ridx[k]] = rc.scale * (st[k].mref + log2f(st[k].s.x + st[k].s.y));
+          (own ? potS : potC)[ridx[k]] = rc.scale * (st[k].mref + lg2_approx(st[k].s.x + st[k].s.y));
         }
       }
     }
