@@ -304,6 +304,9 @@ def host_e2e(batch, dev_index, steps, warmup, barrier):
     barrier()
     h2d, d2h = ctypes.c_size_t(0), ctypes.c_size_t(0)
     L.kdot_host_ctx_last_traffic(ctx, ctypes.byref(h2d), ctypes.byref(d2h))
+    phases = (ctypes.c_double * 4)()
+    L.kdot_host_ctx_last_timing(ctx, phases)
+    host_e2e.last_phases = dict(zip(("pack_us", "enqueue_us", "sync_us", "unpack_us"), [round(v, 2) for v in phases]))
     n_valid = int((valid == 1).sum())
     mean_loss = float(loss.sum() / max(n_valid, 1))
     L.kdot_host_ctx_destroy(ctx)
@@ -395,7 +398,8 @@ def main():
     e2e_dt, h2d, d2h, mean_loss = host_e2e(batch, local_rank, args.steps, args.warmup, barrier)
     e2e_dt = max_over_ranks(e2e_dt)
     e2e = {"value": nimg * world * args.steps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_dt / args.steps * 1e3, "mean_kd_loss": mean_loss}
+           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_dt / args.steps * 1e3, "mean_kd_loss": mean_loss,
+           "last_call_phases": getattr(host_e2e, "last_phases", None)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

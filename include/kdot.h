@@ -110,6 +110,8 @@ int kdot_sinkhorn_fwd_bwd_host(kdot_host_ctx* ctx, float* xs_h, const float* ws_
                                int normalize, int write_back_normalized,
                                float* loss_per_img_h, int32_t* valid_h, float* grad_xs_h,
                                float* grad_ws_h, int32_t* nits_h);
+/* host wall-clock (microseconds) of the last host call's phases: pack, enqueue, synchronise, unpack */
+void kdot_host_ctx_last_timing(const kdot_host_ctx* ctx, double* us4);
 /* bytes moved by the last host call (for bench.py's e2e accounting) */
 void kdot_host_ctx_last_traffic(const kdot_host_ctx* ctx, size_t* h2d_bytes, size_t* d2h_bytes);
 

@@ -18,7 +18,7 @@ KDOT_MAX_ROUNDS = 1024
 # every symbol include/kdot.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = (
     "kdot_sinkhorn_fwd_bwd", "kdot_workspace_bytes", "kdot_host_ctx_create", "kdot_host_ctx_destroy",
-    "kdot_sinkhorn_fwd_bwd_host", "kdot_host_ctx_last_traffic", "kdot_select_cells", "kdot_last_error",
+    "kdot_sinkhorn_fwd_bwd_host", "kdot_host_ctx_last_traffic", "kdot_host_ctx_last_timing", "kdot_select_cells", "kdot_last_error",
     "kdot_version", "kdot_launch_count", "kdot_measure_fp32_peak_tflops", "kdot_debug_set_clock_buffer",
 )
 
@@ -54,6 +54,7 @@ def lib():
     L.kdot_host_ctx_create.argtypes = [i32] * 6
     L.kdot_host_ctx_destroy.argtypes = [vp]
     L.kdot_host_ctx_last_traffic.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
+    L.kdot_host_ctx_last_timing.argtypes = [vp, C.POINTER(C.c_double)]
     L.kdot_sinkhorn_fwd_bwd_host.restype = i32
     L.kdot_sinkhorn_fwd_bwd_host.argtypes = [vp] * 7 + [i32] + [f32] * 6 + [i32, i32] + [vp] * 5
     L.kdot_select_cells.restype = i32

@@ -1,6 +1,8 @@
 // C-ABI entry points of libkdot.so (see include/kdot.h for the contract and the reference citations).
 #include <atomic>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -148,8 +150,11 @@ struct kdot_host_ctx {
   int device, max_img, max_s, max_t, B, D;
   cudaStream_t stream;
   char* pin_in; char* pin_out; char* dev_in; char* dev_out; char* dev_ws;
+  char* pin_in_dev; char* pin_out_dev;  // device-side aliases of the pinned staging areas (zero-copy outputs)
+  int zero_copy;
   size_t cap_in, cap_out, cap_ws;
   size_t last_h2d, last_d2h;
+  double t_pack, t_enqueue, t_sync, t_unpack;  // host wall-clock of the last call's phases, microseconds
 };
 
 kdot_host_ctx* kdot_host_ctx_create(int device, int max_img, int max_cells_s, int max_cells_t, int B, int D) {
@@ -175,6 +180,12 @@ kdot_host_ctx* kdot_host_ctx_create(int device, int max_img, int max_cells_s, in
             cudaMalloc((void**)&c->dev_in, c->cap_in) == cudaSuccess &&
             cudaMalloc((void**)&c->dev_out, c->cap_out) == cudaSuccess &&
             cudaMalloc((void**)&c->dev_ws, c->cap_ws) == cudaSuccess;
+  if (ok) {
+    const char* env = getenv("KDOT_HOST_ZERO_COPY");
+    c->zero_copy = !(env && env[0] == '0') &&
+                   cudaHostGetDevicePointer((void**)&c->pin_in_dev, c->pin_in, 0) == cudaSuccess &&
+                   cudaHostGetDevicePointer((void**)&c->pin_out_dev, c->pin_out, 0) == cudaSuccess;
+  }
   if (!ok) {
     g_err = std::string("kdot_host_ctx_create: ") + cudaGetErrorString(cudaGetLastError());
     kdot_host_ctx_destroy(c);
@@ -192,6 +203,11 @@ void kdot_host_ctx_destroy(kdot_host_ctx* c) {
   if (c->dev_ws) cudaFree(c->dev_ws);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
+}
+
+void kdot_host_ctx_last_timing(const kdot_host_ctx* c, double* us4) {
+  if (!c || !us4) return;
+  us4[0] = c->t_pack; us4[1] = c->t_enqueue; us4[2] = c->t_sync; us4[3] = c->t_unpack;
 }
 
 void kdot_host_ctx_last_traffic(const kdot_host_ctx* c, size_t* h2d, size_t* d2h) {
@@ -220,6 +236,7 @@ int kdot_sinkhorn_fwd_bwd_host(kdot_host_ctx* c, float* xs_h, const float* ws_h,
   if (sn > c->max_s || sm > c->max_t) return fail(KDOT_E_BADARG, "more cells than the context was created for");
   if (cudaSetDevice(c->device) != cudaSuccess) return fail(KDOT_E_CUDA, "cudaSetDevice");
 
+  const auto t0 = std::chrono::steady_clock::now();
   // ---- pack inputs into pinned staging: xs | xt | ws | wt | cu_n | cu_m (each 16-byte aligned) ----
   size_t o = 0;
   const size_t b_xs = (size_t)sn * B * D * sizeof(float), b_xt = (size_t)sm * B * D * sizeof(float);
@@ -249,26 +266,37 @@ int kdot_sinkhorn_fwd_bwd_host(kdot_host_ctx* c, float* xs_h, const float* ws_h,
   const size_t q_gw = q; q = align_up(q + b_ws, 16);
   const size_t out_bytes = q;
 
+  const auto t1 = std::chrono::steady_clock::now();
+  // Inputs go through ONE copy-engine H2D transfer (the kernel re-reads them, so they must sit in HBM).  Small
+  // outputs are written by the kernel straight into the mapped pinned staging area (posted PCIe writes): that
+  // removes the D2H copy-engine launch (~8-10 us of fixed latency) from the critical path.  KDOT_HOST_ZERO_COPY=0
+  // restores the explicit D2H copy; larger outputs always use it.
+  const bool zc_out = c->zero_copy && out_bytes <= (1u << 20) && !(normalize && write_back_normalized);
+  char* out_base = zc_out ? c->pin_out_dev : c->dev_out;
   cudaError_t e = cudaMemcpyAsync(c->dev_in, c->pin_in, in_bytes, cudaMemcpyHostToDevice, c->stream);
   if (e != cudaSuccess) return fail_cuda(e, "H2D");
   int rc = kdot_sinkhorn_fwd_bwd((float*)(c->dev_in + o_xs), ws_h ? (const float*)(c->dev_in + o_ws) : nullptr,
                                  (float*)(c->dev_in + o_xt), wt_h ? (const float*)(c->dev_in + o_wt) : nullptr,
                                  (const int32_t*)(c->dev_in + o_cn), (const int32_t*)(c->dev_in + o_cm), nimg, B, D,
                                  max_n, max_m, KDOT_LAYOUT_CELL_MAJOR, p, blur, reach, scaling, w, h, normalize,
-                                 (float*)(c->dev_out + q_loss), nullptr, (int32_t*)(c->dev_out + q_valid),
-                                 (float*)(c->dev_out + q_gx), (float*)(c->dev_out + q_gw),
-                                 (int32_t*)(c->dev_out + q_nits), c->dev_ws, c->cap_ws, c->stream);
+                                 (float*)(out_base + q_loss), nullptr, (int32_t*)(out_base + q_valid),
+                                 (float*)(out_base + q_gx), (float*)(out_base + q_gw),
+                                 (int32_t*)(out_base + q_nits), c->dev_ws, c->cap_ws, c->stream);
   if (rc != KDOT_OK) return rc;
-  e = cudaMemcpyAsync(c->pin_out, c->dev_out, out_bytes, cudaMemcpyDeviceToHost, c->stream);
-  if (e != cudaSuccess) return fail_cuda(e, "D2H");
   size_t d2h = out_bytes;
-  if (normalize && write_back_normalized) {
-    e = cudaMemcpyAsync(c->pin_in, c->dev_in, o_ws, cudaMemcpyDeviceToHost, c->stream);  // xs | xt normalised
-    if (e != cudaSuccess) return fail_cuda(e, "D2H normalised");
-    d2h += o_ws;
+  if (!zc_out) {
+    e = cudaMemcpyAsync(c->pin_out, c->dev_out, out_bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "D2H");
+    if (normalize && write_back_normalized) {
+      e = cudaMemcpyAsync(c->pin_in, c->dev_in, o_ws, cudaMemcpyDeviceToHost, c->stream);  // xs | xt normalised
+      if (e != cudaSuccess) return fail_cuda(e, "D2H normalised");
+      d2h += o_ws;
+    }
   }
+  const auto t2 = std::chrono::steady_clock::now();
   e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) return fail_cuda(e, "stream sync");
+  const auto t3 = std::chrono::steady_clock::now();
   memcpy(loss_per_img_h, c->pin_out + q_loss, (size_t)nimg * sizeof(float));
   memcpy(valid_h, c->pin_out + q_valid, (size_t)nimg * sizeof(int32_t));
   if (nits_h) memcpy(nits_h, c->pin_out + q_nits, (size_t)nimg * sizeof(int32_t));
@@ -278,6 +306,11 @@ int kdot_sinkhorn_fwd_bwd_host(kdot_host_ctx* c, float* xs_h, const float* ws_h,
     memcpy(xs_h, c->pin_in + o_xs, b_xs);
     memcpy(xt_h, c->pin_in + o_xt, b_xt);
   }
+  const auto t4 = std::chrono::steady_clock::now();
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::micro>(b - a).count();
+  };
+  c->t_pack = us(t0, t1); c->t_enqueue = us(t1, t2); c->t_sync = us(t2, t3); c->t_unpack = us(t3, t4);
   c->last_h2d = in_bytes;
   c->last_d2h = d2h;
   return KDOT_OK;

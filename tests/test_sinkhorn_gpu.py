@@ -80,3 +80,61 @@ def test_tiled_kernel_mixed_with_empty():
 
 def test_tiled_kernel_dense_one_image():
     check(ot_batch(1, seed=1, dense=(1360, 1364), sigma=0.1))
+
+
+@pytest.mark.parametrize("kind", ["small_zero_copy", "small_zero_copy_nowb", "small_memcpy", "tiled"])
+def test_host_buffer_entry_point_matches_device_path(kind, monkeypatch):
+    """kdot_sinkhorn_fwd_bwd_host (host NumPy buffers in/out) is bit-identical to the device-pointer call."""
+    import ctypes
+
+    from kd_6d_pose_adlp_b200 import _lib
+
+    monkeypatch.setenv("KDOT_HOST_ZERO_COPY", "1" if kind.startswith("small_zero_copy") else "0")
+    wb = 0 if kind.endswith("nowb") else 1
+    batch = ot_batch(9, seed=21) if kind != "tiled" else ot_batch(3, seed=22, n_range=(40, 70), m_range=(40, 70))
+    g = run_gpu(batch)
+    L = _lib.lib()
+    nimg = len(batch["pos_per_img"])
+    sn, sm = batch["xs"].shape[0], batch["xt"].shape[0]
+    ctx = L.kdot_host_ctx_create(0, nimg, sn, sm, 8, 2)
+    assert ctx, L.kdot_last_error()
+    xs, xt = batch["xs"].copy(), batch["xt"].copy()
+    pn, pm = np.asarray(batch["pos_per_img"], np.int32), np.asarray(batch["pos_per_img_t"], np.int32)
+    loss, valid, nits = np.empty(nimg, np.float32), np.empty(nimg, np.int32), np.empty(nimg, np.int32)
+    gx, gw = np.empty_like(xs), np.empty_like(batch["ws"])
+    p = lambda a: a.ctypes.data
+    rc = L.kdot_sinkhorn_fwd_bwd_host(ctx, p(xs), p(batch["ws"]), p(xt), p(batch["wt"]), p(pn), p(pm), nimg, 2.0, 0.001, 0.5,
+                                      0.5, 640.0, 480.0, 1, wb, p(loss), p(valid), p(gx), p(gw), p(nits))
+    assert rc == 0, L.kdot_last_error()
+    h2d, d2h = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    L.kdot_host_ctx_last_traffic(ctx, ctypes.byref(h2d), ctypes.byref(d2h))
+    L.kdot_host_ctx_destroy(ctx)
+    assert h2d.value >= xs.nbytes + xt.nbytes and d2h.value >= gx.nbytes
+    np.testing.assert_array_equal(loss, g["loss_per_img"])
+    np.testing.assert_array_equal(valid, g["valid"])
+    np.testing.assert_array_equal(nits, g["nits"])
+    np.testing.assert_array_equal(gx, g["grad_xs"])
+    np.testing.assert_array_equal(gw, g["grad_ws"])
+    if wb:
+        np.testing.assert_array_equal(xs, g["xs_norm"])      # write_back_normalized
+        np.testing.assert_array_equal(xt, g["xt_norm"])
+    else:
+        np.testing.assert_array_equal(xs, batch["xs"])
+
+
+def test_bad_arguments_fail_loudly():
+    from kd_6d_pose_adlp_b200 import _lib
+    from kd_6d_pose_adlp_b200.ops import OTConfig, ot_loss_batched
+
+    dev = torch.device("cuda:0")
+    b = ot_batch(2, seed=0)
+    t = {k: torch.from_numpy(b[k]).to(dev) for k in ("xs", "ws", "xt", "wt")}
+    with pytest.raises(_lib.KdotError, match="p == 2"):
+        ot_loss_batched(t["xs"], t["ws"], t["xt"], t["wt"], b["pos_per_img"], b["pos_per_img_t"], OTConfig(p=1.0))
+    with pytest.raises(ValueError):
+        ot_loss_batched(t["xs"], t["ws"], t["xt"], t["wt"], b["pos_per_img"][:-1] + [999], b["pos_per_img_t"])
+    # clouds too large for the shared-memory plan are refused, not silently mis-computed
+    big = ot_batch(1, seed=0, dense=(4000, 4000))
+    tb = {k: torch.from_numpy(big[k]).to(dev) for k in ("xs", "ws", "xt", "wt")}
+    with pytest.raises(_lib.KdotError, match="shared memory"):
+        ot_loss_batched(tb["xs"], tb["ws"], tb["xt"], tb["wt"], big["pos_per_img"], big["pos_per_img_t"])
