@@ -15,6 +15,9 @@ cudaError_t launch_small(const SinkhornParams& prm, int max_n, int max_m, cudaSt
 cudaError_t launch_tiled(const SinkhornParams& prm, int max_n, int max_m, cudaStream_t stream, size_t smem_limit,
                          bool* too_large);
 size_t tiled_smem_bytes(int max_n, int max_m);
+cudaError_t launch_stream(const SinkhornParams& prm, int D, int max_n, int max_m, void* workspace, cudaStream_t stream);
+size_t stream_workspace_bytes(int nimg, int max_n, int max_m, int B, int D);
+bool stream_supports_dim(int D);
 
 static thread_local std::string g_err;
 static std::atomic<unsigned long long> g_launches{0};
@@ -32,7 +35,17 @@ void count_launches(unsigned n) { g_launches.fetch_add(n, std::memory_order_rela
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static bool small_path(int max_n, int max_m, int B) { return max_n + max_m <= 64 && B <= 16; }
+static size_t device_smem_limit_hint();
+static bool small_path(int max_n, int max_m, int B, int D = 2) { return D == 2 && max_n + max_m <= 64 && B <= 16; }
+
+// 0 = tiled (one CTA per problem, cloud resident in shared memory), 1 = streaming cooperative kernel
+static int large_path(int max_n, int max_m, int D) {
+  const char* env = getenv("KDOT_FORCE_PATH");
+  const bool fits = D == 2 && tiled_smem_bytes(max_n, max_m) <= device_smem_limit_hint();
+  if (env && env[0] == 's') return 1;
+  if (env && env[0] == 't' && fits) return 0;
+  return fits ? 0 : 1;
+}
 
 struct WorkspacePlan {
   size_t off_sched, off_rounds, off_slot, off_ctr, total;
@@ -48,6 +61,7 @@ static WorkspacePlan plan_workspace(int nimg, int B) {
   return w;
 }
 
+static size_t device_smem_limit_hint() { return 227 * 1024; }
 static size_t device_smem_limit() {
   static size_t lim = 0;
   if (lim == 0) {
@@ -70,9 +84,9 @@ void kdot_debug_set_clock_buffer(void* dev_ptr) { g_dbg_clk = (long long*)dev_pt
 unsigned long long kdot_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 size_t kdot_workspace_bytes(int nimg, int max_n, int max_m, int B, int D) {
-  (void)D;
-  if (nimg <= 0 || small_path(max_n, max_m, B)) return 0;
-  return plan_workspace(nimg, B).total;
+  if (nimg <= 0 || small_path(max_n, max_m, B, D)) return 0;
+  if (large_path(max_n, max_m, D) == 0) return plan_workspace(nimg, B).total;
+  return stream_supports_dim(D) ? stream_workspace_bytes(nimg, max_n, max_m, B, D) : 0;
 }
 
 int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt, const int32_t* cu_n,
@@ -84,7 +98,8 @@ int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt
   if (nimg < 0 || B <= 0 || max_n < 0 || max_m < 0) return fail(KDOT_E_BADARG, "negative size");
   if (!xs || !xt || !cu_n || !cu_m || !loss_per_img || !valid || !grad_xs)
     return fail(KDOT_E_BADARG, "NULL required pointer");
-  if (D != 2) return fail(KDOT_E_BADARG, "only D == 2 is implemented by this build");
+  if (!stream_supports_dim(D)) return fail(KDOT_E_BADARG, "D must be one of 1, 2, 3, 4, 8, 16");
+  if (normalize && D != 2) return fail(KDOT_E_BADARG, "normalize requires D == 2 (losses/loss_libs.py:7)");
   if (p != 2.0f) return fail(KDOT_E_BADARG, "only p == 2 is implemented");
   if (!(blur > 0.f) || !(scaling > 0.f && scaling < 1.f)) return fail(KDOT_E_BADARG, "blur > 0 and 0 < scaling < 1 required");
   if (layout != KDOT_LAYOUT_CELL_MAJOR && layout != KDOT_LAYOUT_SLOT_MAJOR) return fail(KDOT_E_BADARG, "bad layout");
@@ -117,14 +132,21 @@ int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt
   prm.dbg_clk = g_dbg_clk;
   cudaStream_t stream = (cudaStream_t)cuda_stream;
 
-  if (small_path(max_n, max_m, B)) {
+  if (small_path(max_n, max_m, B, D)) {
     cudaError_t e = launch_small(prm, max_n, max_m, stream);
     if (e != cudaSuccess) return fail_cuda(e, "kdot_small_kernel");
     count_launches(1);
     return KDOT_OK;
   }
+  const size_t need = kdot_workspace_bytes(nimg, max_n, max_m, B, D);
+  if (!workspace || workspace_bytes < need) return fail(KDOT_E_WORKSPACE, "workspace too small (see kdot_workspace_bytes)");
+  if (large_path(max_n, max_m, D) == 1) {
+    cudaError_t e = launch_stream(prm, D, max_n, max_m, workspace, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "kdot_stream_kernel");
+    count_launches(1);
+    return KDOT_OK;
+  }
   const WorkspacePlan wp = plan_workspace(nimg, B);
-  if (!workspace || workspace_bytes < wp.total) return fail(KDOT_E_WORKSPACE, "workspace too small (see kdot_workspace_bytes)");
   char* base = (char*)workspace;
   prm.sched = (RoundConst*)(base + wp.off_sched);
   prm.sched_rounds = (int32_t*)(base + wp.off_rounds);
@@ -132,12 +154,7 @@ int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt
   prm.done_ctr = (unsigned int*)(base + wp.off_ctr);
   bool too_large = false;
   cudaError_t e = launch_tiled(prm, max_n, max_m, stream, device_smem_limit(), &too_large);
-  if (too_large) {
-    char buf[160];
-    snprintf(buf, sizeof buf, "clouds of %d + %d cells need %zu B of shared memory (limit %zu)", max_n, max_m,
-             tiled_smem_bytes(max_n, max_m), device_smem_limit());
-    return fail(KDOT_E_TOOLARGE, buf);
-  }
+  if (too_large) return fail(KDOT_E_TOOLARGE, "cloud does not fit the tiled kernel's shared-memory plan");
   if (e != cudaSuccess) return fail_cuda(e, "kdot_tiled_kernel");
   count_launches(2);
   return KDOT_OK;
@@ -173,7 +190,11 @@ kdot_host_ctx* kdot_host_ctx_create(int device, int max_img, int max_cells_s, in
   c->cap_in = align_up(pts * (D + 1) * sizeof(float) + 2 * (size_t)(max_img + 1) * sizeof(int32_t) + 1024, 256);
   c->cap_out = align_up((size_t)max_img * 3 * sizeof(float) + (size_t)max_cells_s * B * (D + 1) * sizeof(float) +
                             pts * D * sizeof(float) + 1024, 256);
-  c->cap_ws = plan_workspace(max_img, B).total;
+  {
+    const size_t a = plan_workspace(max_img, B).total;
+    const size_t b2 = stream_supports_dim(D) ? stream_workspace_bytes(max_img, max_cells_s, max_cells_t, B, D) : 0;
+    c->cap_ws = a > b2 ? a : b2;  // worst case: one image holds every cell
+  }
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMallocHost((void**)&c->pin_in, c->cap_in) == cudaSuccess &&
             cudaMallocHost((void**)&c->pin_out, c->cap_out) == cudaSuccess &&

@@ -1,0 +1,481 @@
+// Fused OT distillation loss, streaming kernel: any cloud size, any feature dimension D in {1,2,3,4,8,16}.
+//
+// Same reference code as the other Sinkhorn kernels (losses/loss_libs.py:8-12,22-50 + geomloss' tensorized
+// Sinkhorn divergence + autograd backward), for problems that do not fit one SM's shared memory and for the dense
+// ZebraPose-style 16-D configuration (BASELINE.json configs[3]).  ONE cooperative launch for the whole mini-batch:
+//
+//   phase 0a  per image: in-place normalisation, bounding box, float64 epsilon schedule
+//   phase 0b  stage every (image, slot) problem once into an L2-resident SoA scratch  pts[prob][d][P], lw[prob][P],
+//             h^S/h^C[prob][2][P]  (coalesced, 16-byte aligned column chunks, pads carry h = -big)
+//   rounds    all problems advance in lock-step (grid barrier per round).  A round is a flat queue of WARP units
+//             (problem, row cloud, 32*R-row block, column set); warps of the persistent grid pull units from a
+//             global counter, so the chip stays balanced for any number / size of problems.  A warp streams the
+//             unit's columns straight from L1/L2 with uniform (broadcast) 128-bit loads -- no shared memory, no
+//             intra-CTA barrier -- and evaluates the pairs exactly like the tiled kernel: direct differences,
+//             log2-domain soft-min argument, lazily re-based online max, one ex2 per pair, packed f32x2 math.
+//   final     fixed-order fp64 reduction of the per-row loss terms (bit-reproducible).
+//
+// Potentials never leave the chip's L2 between rounds; the N x M cost matrix is never materialised.
+#include <cooperative_groups.h>
+
+#include "kdot_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace kdot {
+
+constexpr int kStreamThreads = 256;
+constexpr float kTauS = 24.f;
+
+struct StreamParams {
+  SinkhornParams b;
+  int D;
+  int strideP;   // padded points per problem (NqMax + MqMax)
+  int nqMax;     // offset of the teacher block inside a problem
+  int nbx, nby;  // row blocks per cloud (upper bound over the batch), block = 32 * R rows
+  int upp;       // units per problem per round = 2 * (nbx + nby)
+  float* pts;    // [nprob][D][strideP]
+  float* lw2;    // [nprob][strideP]
+  float* pot;    // [nprob][2][strideP]          S, C
+  float* h;      // [nprob][2 buffers][2][strideP]
+  float* term;   // [nprob][strideP]             weight * loss term of every row (final round)
+  unsigned int* ctr;  // [KDOT_MAX_ROUNDS]       unit queue heads, one per round
+};
+
+template <int D, int R, bool GRAD>
+struct URow {
+  float nx[D];          // -p_i
+  float mref, thr;
+  float2 nm;
+  float2 s;
+  float2 g[GRAD ? D : 1];
+};
+
+// R rows of this lane against columns [c0, c1) of one problem (c0, c1 multiples of 4; SoA global arrays).
+template <int D, int R, bool GRAD>
+__device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const float* __restrict__ pts, int strideP,
+                                            const float* __restrict__ ch, int c0, int c1, float coef) {
+  const float2 coef2 = make_float2(coef, coef);
+  for (int j = c0; j < c1; j += 4) {
+    float4 X[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) X[d] = __ldg(reinterpret_cast<const float4*>(pts + (size_t)d * strideP + j));
+    const float4 H = __ldg(reinterpret_cast<const float4*>(ch + j));
+    float2 v0[R], v1[R];
+    bool rebase = false;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      float2 q0 = make_float2(0.f, 0.f), q1 = q0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float2 nd = make_float2(st[k].nx[d], st[k].nx[d]);
+        const float2 a0 = __fadd2_rn(make_float2(X[d].x, X[d].y), nd);
+        const float2 a1 = __fadd2_rn(make_float2(X[d].z, X[d].w), nd);
+        q0 = d == 0 ? __fmul2_rn(a0, a0) : __ffma2_rn(a0, a0, q0);
+        q1 = d == 0 ? __fmul2_rn(a1, a1) : __ffma2_rn(a1, a1, q1);
+      }
+      v0[k] = __ffma2_rn(q0, coef2, make_float2(H.x, H.y));
+      v1[k] = __ffma2_rn(q1, coef2, make_float2(H.z, H.w));
+      const float vm = fmaxf(fmaxf(v0[k].x, v0[k].y), fmaxf(v1[k].x, v1[k].y));
+      rebase |= vm > st[k].thr;
+    }
+    if (rebase) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const float vm = fmaxf(fmaxf(v0[k].x, v0[k].y), fmaxf(v1[k].x, v1[k].y));
+        if (vm > st[k].thr) {
+          const float sc = ex2_approx(st[k].mref - vm);
+          st[k].s.x *= sc; st[k].s.y *= sc;
+          if (GRAD) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) { st[k].g[d].x *= sc; st[k].g[d].y *= sc; }
+          }
+          st[k].mref = vm;
+          st[k].thr = vm + kTauS;
+          st[k].nm = make_float2(-vm, -vm);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const float2 a0 = __fadd2_rn(v0[k], st[k].nm);
+      const float2 a1 = __fadd2_rn(v1[k], st[k].nm);
+      const float2 p0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
+      const float2 p1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+      st[k].s = __fadd2_rn(st[k].s, __fadd2_rn(p0, p1));
+      if (GRAD) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float2 nd = make_float2(st[k].nx[d], st[k].nx[d]);
+          st[k].g[d] = __ffma2_rn(p0, __fadd2_rn(make_float2(X[d].x, X[d].y), nd), st[k].g[d]);
+          st[k].g[d] = __ffma2_rn(p1, __fadd2_rn(make_float2(X[d].z, X[d].w), nd), st[k].g[d]);
+        }
+      }
+    }
+  }
+}
+
+template <int D, int R, bool GRAD>
+__device__ __forceinline__ void urow_reset(URow<D, R, GRAD> (&st)[R]) {
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    st[k].mref = kNegBig;
+    st[k].thr = kNegBig;
+    st[k].nm = make_float2(-kNegBig, -kNegBig);
+    st[k].s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int d = 0; d < (GRAD ? D : 1); ++d) st[k].g[d] = make_float2(0.f, 0.f);
+  }
+}
+
+__device__ __forceinline__ long long cell_index(const SinkhornParams& b, bool student, int cell, int slot) {
+  return student ? (long long)cell * b.s_cell_n + (long long)slot * b.s_slot_n
+                 : (long long)cell * b.s_cell_m + (long long)slot * b.s_slot_m;
+}
+
+template <int D, int R>
+__global__ void __launch_bounds__(kStreamThreads, 2) kdot_stream_kernel(StreamParams p) {
+  cg::grid_group grid = cg::this_grid();
+  const SinkhornParams& b = p.b;
+  const int B = b.B;
+  const int nprob = b.nimg * B;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int strideP = p.strideP;
+  __shared__ float s_box[kStreamThreads / 32][2 * D];
+  __shared__ int s_info[2];
+  __shared__ ImgSched s_is;
+
+  // ---------------- phase 0a: per image normalise / bbox / schedule ----------------
+  for (int img = blockIdx.x; img < b.nimg; img += gridDim.x) {
+    const int n0 = b.cu_n[img], N = b.cu_n[img + 1] - n0;
+    const int m0 = b.cu_m[img], M = b.cu_m[img + 1] - m0;
+    float mn[D], mx[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { mn[d] = 3.0e38f; mx[d] = -3.0e38f; }
+    for (int t = threadIdx.x; t < (N + M) * B; t += blockDim.x) {
+      const int q = t / B, slot = t - q * B;
+      const bool stu = q < N;
+      float* base = stu ? b.xs : b.xt;
+      const long long g = cell_index(b, stu, stu ? n0 + q : m0 + q - N, slot);
+      float v[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) v[d] = base[(size_t)D * g + d];
+      if (b.normalize && D == 2) {
+        v[0] = __fdiv_rn(v[0], b.w);
+        v[D - 1] = __fdiv_rn(v[D - 1], b.h);
+        base[(size_t)D * g] = v[0];
+        base[(size_t)D * g + D - 1] = v[D - 1];
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) { mn[d] = fminf(mn[d], v[d]); mx[d] = fmaxf(mx[d], v[d]); }
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) { mn[d] = warp_min(mn[d]); mx[d] = warp_max(mx[d]); }
+    if (lane == 0) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) { s_box[warp][d] = mn[d]; s_box[warp][D + d] = mx[d]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        float lo = s_box[0][d], hi = s_box[0][D + d];
+        for (int wi = 1; wi < nwarps; ++wi) { lo = fminf(lo, s_box[wi][d]); hi = fmaxf(hi, s_box[wi][D + d]); }
+        const float e = __fsub_rn(hi, lo);
+        acc = __fadd_rn(acc, __fmul_rn(e, e));
+      }
+      int status = KDOT_IMG_OK, nits = 0;
+      if (N == 0 || M == 0) {
+        status = KDOT_IMG_SKIPPED;
+      } else {
+        const float diam = sqrtf(acc);
+        if (!(diam > 0.f) || !isfinite(diam)) {
+          status = KDOT_IMG_DEGENERATE;
+        } else {
+          s_is = image_schedule(diam, b.sp);
+          nits = s_is.nits;
+          if (nits + 2 > KDOT_MAX_ROUNDS) status = KDOT_IMG_TOO_MANY_ROUNDS;
+        }
+      }
+      s_info[0] = status;
+      s_info[1] = nits;
+      b.sched_rounds[img] = status == KDOT_IMG_OK ? nits + 2 : 0;
+      b.valid[img] = status;
+      if (b.nits_per_img) b.nits_per_img[img] = nits;
+      if (status != KDOT_IMG_OK) b.loss_per_img[img] = status == KDOT_IMG_SKIPPED ? 0.f : __int_as_float(0x7fc00000);
+    }
+    __syncthreads();
+    const int status = s_info[0], nits = s_info[1];
+    if (status == KDOT_IMG_OK) {
+      for (int r = threadIdx.x; r < nits + 2; r += blockDim.x)
+        b.sched[(size_t)img * KDOT_MAX_ROUNDS + r] = make_round_const(r, s_is, b.sp);
+    } else {
+      const float fill = status == KDOT_IMG_SKIPPED ? 0.f : __int_as_float(0x7fc00000);
+      for (int t = threadIdx.x; t < N * B; t += blockDim.x) {
+        const int q = t / B, slot = t - q * B;
+        const long long g = cell_index(b, true, n0 + q, slot);
+#pragma unroll
+        for (int d = 0; d < D; ++d) b.grad_xs[(size_t)D * g + d] = fill;
+        if (b.grad_ws) b.grad_ws[g] = fill;
+      }
+      if (b.loss_per_slot)
+        for (int s = threadIdx.x; s < B; s += blockDim.x) b.loss_per_slot[(size_t)img * B + s] = fill;
+    }
+    __syncthreads();
+  }
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < KDOT_MAX_ROUNDS; r += gridDim.x * blockDim.x) p.ctr[r] = 0u;
+  grid.sync();
+
+  // ---------------- phase 0b: stage problems (SoA, padded) ----------------
+  int max_rounds = 0;
+  for (int i = 0; i < b.nimg; ++i) max_rounds = max(max_rounds, b.sched_rounds[i]);
+  {
+    const long long total = (long long)nprob * strideP;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+      const int prob = (int)(t / strideP), q = (int)(t - (long long)prob * strideP);
+      const int img = prob / B, slot = prob - img * B;
+      if (b.sched_rounds[img] <= 0) continue;
+      const int n0 = b.cu_n[img], N = b.cu_n[img + 1] - n0;
+      const int m0 = b.cu_m[img], M = b.cu_m[img + 1] - m0;
+      const bool in_x = q < p.nqMax;
+      const int i = in_x ? q : q - p.nqMax;
+      const bool real = in_x ? (i < N) : (i < M);
+      float l2 = kNegBig;
+      float v[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) v[d] = 0.f;
+      if (real) {
+        const long long g = cell_index(b, in_x, in_x ? n0 + i : m0 + i, slot);
+        const float* base = in_x ? b.xs : b.xt;
+        const float* wb = in_x ? b.ws : b.wt;
+#pragma unroll
+        for (int d = 0; d < D; ++d) v[d] = base[(size_t)D * g + d];
+        const float wg = wb ? wb[g] : __fdiv_rn(1.0f, (float)(in_x ? N : M));
+        l2 = (wg > 0.f ? logf(wg) : kLogZeroWeight) * kLog2e;
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) p.pts[((size_t)prob * D + d) * strideP + q] = v[d];
+      p.lw2[(size_t)prob * strideP + q] = l2;
+      float* hb = p.h + (size_t)prob * 4 * strideP;
+      hb[q] = l2; hb[strideP + q] = l2; hb[2 * strideP + q] = l2; hb[3 * strideP + q] = l2;
+      p.pot[(size_t)prob * 2 * strideP + q] = 0.f;
+      p.pot[(size_t)prob * 2 * strideP + strideP + q] = 0.f;
+      p.term[(size_t)prob * strideP + q] = 0.f;
+    }
+  }
+  grid.sync();
+
+  // ---------------- rounds ----------------
+  const int gwarp = blockIdx.x * nwarps + warp;
+  (void)gwarp;
+  const long long units_total = (long long)nprob * p.upp;
+  const double rho = b.rho;
+  for (int r = 0; r < max_rounds; ++r) {
+    const int cur = r & 1;
+    for (;;) {
+      unsigned int u = 0;
+      if (lane == 0) u = atomicAdd(&p.ctr[r], 1u);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if ((long long)u >= units_total) break;
+      const int prob = (int)(u / p.upp), uu = (int)(u - (unsigned)prob * p.upp);
+      const int img = prob / B, slot = prob - img * B;
+      const int nrounds = b.sched_rounds[img];
+      if (r >= nrounds) continue;  // image finished (or skipped)
+      const bool last = r == nrounds - 1;
+      const int N = b.cu_n[img + 1] - b.cu_n[img], M = b.cu_m[img + 1] - b.cu_m[img];
+      const int Nq = (N + 3) & ~3, Mq = (M + 3) & ~3;
+      const bool rows_x = uu < 2 * p.nbx;
+      const int ub = rows_x ? uu : uu - 2 * p.nbx;
+      const int blk = ub >> 1;
+      const bool own = (ub & 1) == 0;
+      const int rcount = rows_x ? N : M;
+      if (blk * 32 * R >= rcount) continue;  // padded unit of a smaller image
+      const int rbase = rows_x ? 0 : p.nqMax;
+      const RoundConst rc = b.sched[(size_t)img * KDOT_MAX_ROUNDS + r];
+      const float* pts = p.pts + (size_t)prob * D * strideP;
+      const float* lw2 = p.lw2 + (size_t)prob * strideP;
+      float* potS = p.pot + (size_t)prob * 2 * strideP;
+      float* potC = potS + strideP;
+      const float* hSc = p.h + ((size_t)prob * 4 + cur * 2) * strideP;
+      const float* hCc = hSc + strideP;
+      float* hSn = p.h + ((size_t)prob * 4 + (cur ^ 1) * 2) * strideP;
+      float* hCn = hSn + strideP;
+
+      if (last && rows_x) {
+        if (!own) continue;  // the student's last round is done by the "own" unit for both column sets
+        // one row per pass keeps the gradient accumulators in registers for every D
+        for (int k0 = 0; k0 < R; ++k0) {
+          const int i = blk * 32 * R + lane + 32 * k0;
+          const bool act = i < N;
+          const int src = act ? i : 0;
+          URow<D, 1, true> st[1];
+          urow_reset<D, 1, true>(st);
+#pragma unroll
+          for (int d = 0; d < D; ++d) st[0].nx[d] = -pts[(size_t)d * strideP + src];
+          stream_rows<D, 1, true>(st, pts, strideP, hSc, 0, Nq, rc.coef);
+          const float sS = st[0].s.x + st[0].s.y;
+          const float S = rc.scale * (st[0].mref + lg2_approx(sS));
+          float gS[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) gS[d] = (st[0].g[d].x + st[0].g[d].y) / sS;
+          urow_reset<D, 1, true>(st);
+          stream_rows<D, 1, true>(st, pts + p.nqMax, strideP, hCc + p.nqMax, 0, Mq, rc.coef);
+          if (!act) continue;
+          const float sC = st[0].s.x + st[0].s.y;
+          const float C = rc.scale * (st[0].mref + lg2_approx(sC));
+          const RowFinal f = row_final(S, C, rho, rc.eps);
+          const float lam = rho < 0.0 ? 1.f : (float)(1.0 / (1.0 + (double)rc.eps / rho));
+          const float gfac = rho < 0.0 ? 1.f : (float)((rho + 0.5 * (double)rc.eps) / rho) * lam;
+          const long long g = cell_index(b, true, b.cu_n[img] + i, slot);
+          const float wg = b.ws ? b.ws[g] : __fdiv_rn(1.0f, (float)N);
+          p.term[(size_t)prob * strideP + i] = wg * f.term;
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            float gv = wg * gfac * (f.eS * gS[d] - f.eC * ((st[0].g[d].x + st[0].g[d].y) / sC));
+            if (b.normalize && D == 2) gv = __fdiv_rn(gv, d == 0 ? b.w : b.h);
+            b.grad_xs[(size_t)D * g + d] = gv;
+          }
+          if (b.grad_ws) b.grad_ws[g] = f.term;
+        }
+        continue;
+      }
+
+      const bool cols_x = (rows_x == own);
+      const float* cpts = cols_x ? pts : pts + p.nqMax;
+      const float* ch = (own ? hSc : hCc) + (cols_x ? 0 : p.nqMax);
+      const int ncols = cols_x ? Nq : Mq;
+      URow<D, R, false> st[R];
+      urow_reset<D, R, false>(st);
+      int ridx[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int i = blk * 32 * R + lane + 32 * k;
+        ridx[k] = i < rcount ? rbase + i : -1;
+        const int src = ridx[k] >= 0 ? ridx[k] : rbase;
+#pragma unroll
+        for (int d = 0; d < D; ++d) st[k].nx[d] = -pts[(size_t)d * strideP + src];
+      }
+      stream_rows<D, R, false>(st, cpts, strideP, ch, 0, ncols, rc.coef);
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        if (ridx[k] < 0) continue;
+        const float lse = st[k].mref + lg2_approx(st[k].s.x + st[k].s.y);
+        float* pot = own ? potS : potC;
+        const float nv = rc.scale * lse;
+        const float pv = (r == 0 || last) ? nv : 0.5f * (pot[ridx[k]] + nv);
+        pot[ridx[k]] = pv;
+        if (!last) (own ? hSn : hCn)[ridx[k]] = fmaf(pv, rc.hmul, lw2[ridx[k]]);
+      }
+    }
+    grid.sync();
+  }
+
+  // ---------------- final: fixed-order loss reduction, one warp per image ----------------
+  for (int img = blockIdx.x * nwarps + warp; img < b.nimg; img += gridDim.x * nwarps) {
+    const int nrounds = b.sched_rounds[img];
+    if (nrounds <= 0) continue;
+    const int N = b.cu_n[img + 1] - b.cu_n[img], M = b.cu_m[img + 1] - b.cu_m[img];
+    const float eps_last = b.sched[(size_t)img * KDOT_MAX_ROUNDS + nrounds - 1].eps;
+    double tot = 0.0;
+    for (int slot = 0; slot < B; ++slot) {
+      const int prob = img * B + slot;
+      const float* term = p.term + (size_t)prob * strideP;
+      const float* potS = p.pot + (size_t)prob * 2 * strideP;
+      const float* potC = potS + strideP;
+      double acc = 0.0;
+      for (int i = lane; i < N; i += 32) acc += (double)term[i];
+      for (int j = lane; j < M; j += 32) {
+        const RowFinal f = row_final(potS[p.nqMax + j], potC[p.nqMax + j], rho, eps_last);
+        const long long g = cell_index(b, false, b.cu_m[img] + j, slot);
+        const float wg = b.wt ? b.wt[g] : __fdiv_rn(1.0f, (float)M);
+        acc += (double)wg * (double)f.term;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0 && b.loss_per_slot) b.loss_per_slot[(size_t)prob] = (float)acc;
+      tot += acc;
+    }
+    if (lane == 0) b.loss_per_img[img] = (float)tot;
+  }
+}
+
+struct StreamPlan {
+  int strideP, nqMax, nbx, nby, upp, R;
+  size_t off_pts, off_lw, off_pot, off_h, off_term, off_ctr, off_sched, off_rounds, total;
+};
+
+static int rows_per_lane(int D) { return D <= 2 ? 4 : (D <= 8 ? 2 : 1); }
+
+StreamPlan plan_stream(int nimg, int max_n, int max_m, int B, int D) {
+  StreamPlan s;
+  s.R = rows_per_lane(D);
+  s.nqMax = (max_n + 3) & ~3;
+  const int mq = (max_m + 3) & ~3;
+  s.strideP = s.nqMax + mq;
+  s.nbx = (max_n + 32 * s.R - 1) / (32 * s.R);
+  s.nby = (max_m + 32 * s.R - 1) / (32 * s.R);
+  s.upp = 2 * (s.nbx + s.nby);
+  const size_t nprob = (size_t)nimg * B, P = (size_t)s.strideP;
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  size_t o = 0;
+  s.off_pts = o;    o = up(o + nprob * D * P * 4);
+  s.off_lw = o;     o = up(o + nprob * P * 4);
+  s.off_pot = o;    o = up(o + nprob * 2 * P * 4);
+  s.off_h = o;      o = up(o + nprob * 4 * P * 4);
+  s.off_term = o;   o = up(o + nprob * P * 4);
+  s.off_ctr = o;    o = up(o + (size_t)KDOT_MAX_ROUNDS * 4);
+  s.off_sched = o;  o = up(o + (size_t)nimg * KDOT_MAX_ROUNDS * sizeof(RoundConst));
+  s.off_rounds = o; o = up(o + (size_t)nimg * 4);
+  s.total = o;
+  return s;
+}
+
+size_t stream_workspace_bytes(int nimg, int max_n, int max_m, int B, int D) {
+  return plan_stream(nimg, max_n, max_m, B, D).total;
+}
+
+bool stream_supports_dim(int D) { return D == 1 || D == 2 || D == 3 || D == 4 || D == 8 || D == 16; }
+
+template <int D, int R>
+static cudaError_t launch_stream_t(StreamParams& sp, cudaStream_t stream) {
+  static int blocks_per_sm = 0, sms = 0;
+  if (blocks_per_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kdot_stream_kernel<D, R>, kStreamThreads, 0);
+    if (e != cudaSuccess) return e;
+    if (blocks_per_sm < 1) return cudaErrorLaunchOutOfResources;
+  }
+  void* args[] = {&sp};
+  return cudaLaunchCooperativeKernel((const void*)kdot_stream_kernel<D, R>, dim3(blocks_per_sm * sms), dim3(kStreamThreads),
+                                     args, 0, stream);
+}
+
+cudaError_t launch_stream(const SinkhornParams& prm, int D, int max_n, int max_m, void* workspace, cudaStream_t stream) {
+  const StreamPlan pl = plan_stream(prm.nimg, max_n, max_m, prm.B, D);
+  char* base = (char*)workspace;
+  StreamParams sp;
+  sp.b = prm;
+  sp.b.sched = (RoundConst*)(base + pl.off_sched);
+  sp.b.sched_rounds = (int32_t*)(base + pl.off_rounds);
+  sp.D = D;
+  sp.strideP = pl.strideP; sp.nqMax = pl.nqMax; sp.nbx = pl.nbx; sp.nby = pl.nby; sp.upp = pl.upp;
+  sp.pts = (float*)(base + pl.off_pts);
+  sp.lw2 = (float*)(base + pl.off_lw);
+  sp.pot = (float*)(base + pl.off_pot);
+  sp.h = (float*)(base + pl.off_h);
+  sp.term = (float*)(base + pl.off_term);
+  sp.ctr = (unsigned int*)(base + pl.off_ctr);
+  switch (D) {
+    case 1: return launch_stream_t<1, 2>(sp, stream);
+    case 2: return launch_stream_t<2, 4>(sp, stream);
+    case 3: return launch_stream_t<3, 2>(sp, stream);
+    case 4: return launch_stream_t<4, 2>(sp, stream);
+    case 8: return launch_stream_t<8, 2>(sp, stream);
+    case 16: return launch_stream_t<16, 1>(sp, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace kdot

@@ -133,64 +133,62 @@ def test_bad_arguments_fail_loudly():
         ot_loss_batched(t["xs"], t["ws"], t["xt"], t["wt"], b["pos_per_img"], b["pos_per_img_t"], OTConfig(p=1.0))
     with pytest.raises(ValueError):
         ot_loss_batched(t["xs"], t["ws"], t["xt"], t["wt"], b["pos_per_img"][:-1] + [999], b["pos_per_img_t"])
-    # clouds too large for the shared-memory plan are refused, not silently mis-computed
-    big = ot_batch(1, seed=0, dense=(4000, 4000))
-    tb = {k: torch.from_numpy(big[k]).to(dev) for k in ("xs", "ws", "xt", "wt")}
-    with pytest.raises(_lib.KdotError, match="shared memory"):
-        ot_loss_batched(tb["xs"], tb["ws"], tb["xt"], tb["wt"], big["pos_per_img"], big["pos_per_img_t"])
 
 
-@pytest.mark.parametrize("scaling", [0.95, 0.975])
-def test_long_schedules_take_the_log_exp_route(scaling):
-    """> 48 schedule entries (BASELINE.json configs[4]: 100-200 Sinkhorn rounds): device log/exp schedule route."""
-    rows = check(ot_batch(3, seed=13), scaling=scaling)
-    b = ot_batch(2, seed=14, n_range=(40, 50), m_range=(40, 50), p_empty_teacher=0.0)
-    check(b, scaling=scaling)
+def test_stream_kernel_matches_oracle_d2(monkeypatch):
+    """The cooperative streaming kernel on the same D = 2 problems as the tiled kernel (forced path)."""
+    monkeypatch.setenv("KDOT_FORCE_PATH", "stream")
+    check(ot_batch(3, seed=7, n_range=(40, 90), m_range=(50, 120), p_empty_teacher=0.0))
+    check(ot_batch(6, seed=9, n_range=(1, 70), m_range=(1, 70), p_empty_teacher=0.3))
+    check(ot_batch(4, seed=31, n_range=(33, 40), m_range=(33, 40)), reach=None, scaling=0.7)
 
 
-def test_samples_loss_seam_b2_with_autograd():
-    """SamplesLoss(alpha, x, beta, y) -> (B,) on the (B,N,D) layout, gradients to x and alpha (loss_libs.py:47)."""
+def test_stream_kernel_clouds_beyond_shared_memory():
+    """N = M = 3500 cells in one slot: too large for the tiled kernel's shared-memory plan -> streaming kernel."""
+    from kd_6d_pose_adlp_b200.ops import OTConfig, ot_loss_batched
+    from oracle import sinkhorn_analytic
+    from kd_6d_pose_adlp_b200.synthetic import cu_seqlens
+
+    b = ot_batch(1, seed=41, dense=(3500, 3400), B=1, sigma=0.1)
+    dev = torch.device("cuda:0")
+    t = {k: torch.from_numpy(b[k]).to(dev) for k in ("xs", "ws", "xt", "wt")}
+    out = ot_loss_batched(t["xs"], t["ws"], t["xt"], t["wt"], b["pos_per_img"], b["pos_per_img_t"], OTConfig())
+    torch.cuda.synchronize()
+    o = sinkhorn_analytic.kdot_fwd_bwd_f64(b["xs"], b["ws"], b["xt"], b["wt"], cu_seqlens(b["pos_per_img"]),
+                                           cu_seqlens(b["pos_per_img_t"]), 1, 2)
+    assert np.array_equal(out["nits"].cpu().numpy(), o["nits"])
+    assert parity.rel(out["loss_per_img"].cpu().numpy(), o["loss_per_img"]) < 2e-6
+    assert parity.rel(out["grad_ws"].cpu().numpy(), o["grad_ws"]) < 5e-5
+    assert parity.rel(out["grad_xs"].cpu().numpy(), o["grad_xs"]) < 5e-3
+
+
+@pytest.mark.parametrize("D,blur", [(16, 0.05), (16, 0.01), (3, 0.01), (8, 0.001)])
+def test_stream_kernel_generic_dimension(D, blur):
+    """ZebraPose-style per-cell code distributions (BASELINE.json configs[3]): D-dimensional points, one slot."""
     from kd_6d_pose_adlp_b200 import SamplesLoss
     from oracle import geomloss_ref
 
     dev = torch.device("cuda:0")
-    g = torch.Generator().manual_seed(5)
-    for B, N, M in [(8, 10, 12), (1, 7, 5), (3, 50, 40)]:
-        x = (0.5 + 0.05 * torch.randn(B, N, 2, generator=g)).float()
-        y = (0.5 + 0.05 * torch.randn(B, M, 2, generator=g)).float()
-        a = torch.rand(B, N, generator=g) * 0.9 + 0.05
-        b = torch.rand(B, M, generator=g) * 0.9 + 0.05
-        xd, ad = x.to(dev).requires_grad_(True), a.to(dev).requires_grad_(True)
-        out = SamplesLoss("sinkhorn", p=2, blur=0.001, scaling=0.5, reach=0.5)(ad, xd, b.to(dev), y.to(dev))
-        assert out.shape == (B,)
-        wsum = torch.linspace(0.5, 1.5, B, device=dev)
-        (out * wsum).sum().backward()
-        # fp64 oracle through autograd
-        x64, a64 = x.double().requires_grad_(True), a.double().requires_grad_(True)
-        ref = geomloss_ref.SamplesLoss("sinkhorn", p=2, blur=0.001, scaling=0.5, reach=0.5)(a64, x64, b.double(), y.double())
-        (ref * wsum.cpu().double()).sum().backward()
-        assert parity.rel(out.detach().cpu().numpy(), ref.detach().numpy()) < 2e-6
-        assert parity.rel(ad.grad.cpu().numpy(), a64.grad.numpy()) < 2e-5
-        assert parity.rel(xd.grad.cpu().numpy(), x64.grad.numpy()) < 5e-3
-        # unweighted (x, y) call: uniform 1/N, 1/M masses (loss_libs.py:49)
-        out_u = SamplesLoss("sinkhorn", p=2, blur=0.01, scaling=0.5, reach=None)(x.to(dev), y.to(dev))
-        ref_u = geomloss_ref.SamplesLoss("sinkhorn", p=2, blur=0.01, scaling=0.5, reach=None)(x.double(), y.double())
-        assert parity.rel(out_u.cpu().numpy(), ref_u.numpy()) < 2e-6
-
-
-def test_zero_mass_cells_and_status_codes():
-    from kd_6d_pose_adlp_b200 import _lib
-
-    b = ot_batch(4, seed=17, p_empty_teacher=0.0)
-    b["ws"][::3] = 0.0           # zero-mass student cells: log-weight -100000 like geomloss
-    check(b)
-    # an image whose points all coincide has zero diameter: geomloss would raise from np.arange; we flag it
-    d = ot_batch(2, seed=18, p_empty_teacher=0.0)
-    n0 = d["pos_per_img"][0]
-    m0 = d["pos_per_img_t"][0]
-    d["xs"][:n0] = 100.0
-    d["xt"][:m0] = 100.0
-    g = run_gpu(d)
-    assert g["valid"][0] == _lib.KDOT_IMG_DEGENERATE and np.isnan(g["loss_per_img"][0])
-    assert g["valid"][1] == _lib.KDOT_IMG_OK and np.isfinite(g["loss_per_img"][1])
-    assert np.isnan(g["grad_xs"][:n0]).all() and np.isfinite(g["grad_xs"][n0:]).all()
+    g = torch.Generator().manual_seed(D)
+    B, N, M = 2, 150, 170
+    x = torch.sigmoid(torch.randn(B, N, D, generator=g)).float()
+    y = torch.sigmoid(torch.randn(B, M, D, generator=g)).float()
+    a = torch.sigmoid(torch.randn(B, N, generator=g)).float()
+    bb = torch.sigmoid(torch.randn(B, M, generator=g)).float()
+    xd, ad = x.to(dev).requires_grad_(True), a.to(dev).requires_grad_(True)
+    L = SamplesLoss("sinkhorn", p=2, blur=blur, scaling=0.5, reach=0.5)
+    out = L(ad, xd, bb.to(dev), y.to(dev))
+    out.sum().backward()
+    res = {}
+    for name, dt in (("ref32", torch.float32), ("ref64", torch.float64)):
+        xr, ar = x.detach().clone().to(dt).requires_grad_(True), a.detach().clone().to(dt).requires_grad_(True)
+        Lr = geomloss_ref.SamplesLoss("sinkhorn", p=2, blur=blur, scaling=0.5, reach=0.5)
+        o = Lr(ar, xr, bb.to(dt), y.to(dt))
+        o.sum().backward()
+        res[name] = (o.detach().double().numpy(), xr.grad.double().numpy(), ar.grad.double().numpy(), Lr.last_nits)
+    assert int(L.last_nits.cpu()[0]) == res["ref64"][3]
+    rows = [parity.report("loss", out.detach().cpu().numpy(), res["ref32"][0], res["ref64"][0]),
+            parity.report("grad_x", xd.grad.cpu().numpy(), res["ref32"][1], res["ref64"][1]),
+            parity.report("grad_a", ad.grad.cpu().numpy(), res["ref32"][2], res["ref64"][2])]
+    print("\n" + parity.fmt(rows))
+    assert all(r["ok"] for r in rows), parity.fmt(rows)
