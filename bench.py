@@ -313,6 +313,14 @@ def host_e2e(batch, dev_index, steps, warmup, barrier):
     return dt, int(h2d.value), int(d2h.value), mean_loss
 
 
+def kernel_name(max_n, max_m, launches_per_step):
+    if max_n + max_m <= 32:
+        return "kdot_small_fast_kernel"
+    if max_n + max_m <= 64:
+        return "kdot_small_kernel"
+    return "kdot_tiled_kernel" if launches_per_step == 2 else "kdot_stream_kernel"
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -383,7 +391,7 @@ def main():
     flops, exps, byts = algorithmic_work(batch, nits)
     med_ms = statistics.median(per)
     roofline = {
-        "bound": "fp32", "kernel": ("kdot_small_fast_kernel" if bench.max_n + bench.max_m <= 32 else "kdot_small_kernel") if launches == args.steps else "kdot_tiled_kernel",
+        "bound": "fp32", "kernel": kernel_name(bench.max_n, bench.max_m, launches // max(args.steps, 1)),
         "achieved": flops / (ms_per_step * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": flops / (ms_per_step * 1e-3) / 1e12 / fp32_peak if fp32_peak > 0 else None,
         "peak_source": "FP32 FMA chain measured live on this GPU (kdot_measure_fp32_peak_tflops)",

@@ -34,12 +34,13 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("KDOT_LIB", LIB_PATH)  # tuning aid: alternative builds of the same ABI
+    if not os.path.exists(path):
         raise KdotError(
-            f"{LIB_PATH} not found: the CUDA extension is not built and there is no CPU fallback. "
+            f"{path} not found: the CUDA extension is not built and there is no CPU fallback. "
             "Run `python -m kd_6d_pose_adlp_b200.build`."
         )
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
     L.kdot_last_error.restype = C.c_char_p
     L.kdot_version.restype = i32

@@ -40,11 +40,12 @@ static bool small_path(int max_n, int max_m, int B, int D = 2) { return D == 2 &
 
 // 0 = tiled (one CTA per problem, cloud resident in shared memory), 1 = streaming cooperative kernel
 static int large_path(int max_n, int max_m, int D) {
+  // default: the streaming cooperative kernel (chip-wide dynamic balance, any size, any supported D);
+  // KDOT_FORCE_PATH=tiled selects the one-CTA-per-problem shared-memory kernel where it applies (D = 2, cloud fits)
   const char* env = getenv("KDOT_FORCE_PATH");
   const bool fits = D == 2 && tiled_smem_bytes(max_n, max_m) <= device_smem_limit_hint();
-  if (env && env[0] == 's') return 1;
   if (env && env[0] == 't' && fits) return 0;
-  return fits ? 0 : 1;
+  return 1;
 }
 
 struct WorkspacePlan {

@@ -39,32 +39,53 @@ struct StreamParams {
   float* pot;    // [nprob][2][strideP]          S, C
   float* h;      // [nprob][2 buffers][2][strideP]
   float* term;   // [nprob][strideP]             weight * loss term of every row (final round)
-  unsigned int* ctr;  // [KDOT_MAX_ROUNDS]       unit queue heads, one per round
+  unsigned int* ctr;  // [KDOT_MAX_ROUNDS]       first 8 bytes: 64-bit head of the global unit FIFO
+  unsigned int* done; // [nprob]                 finished units per problem (all rounds)
 };
 
 template <int D, int R, bool GRAD>
 struct URow {
   float nx[D];          // -p_i
-  float mref, thr;
+  float mref;
   float2 nm;
   float2 s;
   float2 g[GRAD ? D : 1];
 };
 
-// R rows of this lane against columns [c0, c1) of one problem (c0, c1 multiples of 4; SoA global arrays).
+__device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// One 4-column chunk (X[d] = coordinates, H = soft-min offsets) against the R rows of this lane.
+// Running sums are kept relative to a possibly stale reference exponent mref; a chunk whose partial sum exceeds
+// 2^kTauS (or is +inf: first chunk, mref = -big) takes the cold path that re-bases on the exact max (see
+// kdot_tiled.cu for the full argument).
 template <int D, int R, bool GRAD>
-__device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const float* __restrict__ pts, int strideP,
-                                            const float* __restrict__ ch, int c0, int c1, float coef) {
-  const float2 coef2 = make_float2(coef, coef);
-  for (int j = c0; j < c1; j += 4) {
-    float4 X[D];
+__device__ __forceinline__ void stream_chunk(URow<D, R, GRAD> (&st)[R], const float4 (&X)[D], const float4& H,
+                                             const float2 coef2, const float big) {
+  float2 ps[R], p0s[GRAD ? R : 1], p1s[GRAD ? R : 1];
+  bool rebase = false;
 #pragma unroll
-    for (int d = 0; d < D; ++d) X[d] = __ldg(reinterpret_cast<const float4*>(pts + (size_t)d * strideP + j));
-    const float4 H = __ldg(reinterpret_cast<const float4*>(ch + j));
-    float2 v0[R], v1[R];
-    bool rebase = false;
+  for (int k = 0; k < R; ++k) {
+    float2 q0 = make_float2(0.f, 0.f), q1 = q0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float2 nd = make_float2(st[k].nx[d], st[k].nx[d]);
+      const float2 a0 = __fadd2_rn(make_float2(X[d].x, X[d].y), nd);
+      const float2 a1 = __fadd2_rn(make_float2(X[d].z, X[d].w), nd);
+      q0 = d == 0 ? __fmul2_rn(a0, a0) : __ffma2_rn(a0, a0, q0);
+      q1 = d == 0 ? __fmul2_rn(a1, a1) : __ffma2_rn(a1, a1, q1);
+    }
+    const float2 e0 = __fadd2_rn(__ffma2_rn(q0, coef2, make_float2(H.x, H.y)), st[k].nm);
+    const float2 e1 = __fadd2_rn(__ffma2_rn(q1, coef2, make_float2(H.z, H.w)), st[k].nm);
+    const float2 p0 = make_float2(ex2_approx(e0.x), ex2_approx(e0.y));
+    const float2 p1 = make_float2(ex2_approx(e1.x), ex2_approx(e1.y));
+    ps[k] = __fadd2_rn(p0, p1);
+    if (GRAD) { p0s[k] = p0; p1s[k] = p1; }
+    rebase |= !(ps[k].x + ps[k].y <= big);
+  }
+  if (rebase) {
 #pragma unroll
     for (int k = 0; k < R; ++k) {
+      if (ps[k].x + ps[k].y <= big) continue;
       float2 q0 = make_float2(0.f, 0.f), q1 = q0;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
@@ -74,44 +95,87 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
         q0 = d == 0 ? __fmul2_rn(a0, a0) : __ffma2_rn(a0, a0, q0);
         q1 = d == 0 ? __fmul2_rn(a1, a1) : __ffma2_rn(a1, a1, q1);
       }
-      v0[k] = __ffma2_rn(q0, coef2, make_float2(H.x, H.y));
-      v1[k] = __ffma2_rn(q1, coef2, make_float2(H.z, H.w));
-      const float vm = fmaxf(fmaxf(v0[k].x, v0[k].y), fmaxf(v1[k].x, v1[k].y));
-      rebase |= vm > st[k].thr;
-    }
-    if (rebase) {
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        const float vm = fmaxf(fmaxf(v0[k].x, v0[k].y), fmaxf(v1[k].x, v1[k].y));
-        if (vm > st[k].thr) {
-          const float sc = ex2_approx(st[k].mref - vm);
-          st[k].s.x *= sc; st[k].s.y *= sc;
-          if (GRAD) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) { st[k].g[d].x *= sc; st[k].g[d].y *= sc; }
-          }
-          st[k].mref = vm;
-          st[k].thr = vm + kTauS;
-          st[k].nm = make_float2(-vm, -vm);
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-      const float2 a0 = __fadd2_rn(v0[k], st[k].nm);
-      const float2 a1 = __fadd2_rn(v1[k], st[k].nm);
-      const float2 p0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
-      const float2 p1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
-      st[k].s = __fadd2_rn(st[k].s, __fadd2_rn(p0, p1));
+      const float2 v0 = __ffma2_rn(q0, coef2, make_float2(H.x, H.y));
+      const float2 v1 = __ffma2_rn(q1, coef2, make_float2(H.z, H.w));
+      const float vm = fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y));
+      const float sc = ex2_approx(st[k].mref - vm);
+      st[k].s.x *= sc; st[k].s.y *= sc;
       if (GRAD) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          const float2 nd = make_float2(st[k].nx[d], st[k].nx[d]);
-          st[k].g[d] = __ffma2_rn(p0, __fadd2_rn(make_float2(X[d].x, X[d].y), nd), st[k].g[d]);
-          st[k].g[d] = __ffma2_rn(p1, __fadd2_rn(make_float2(X[d].z, X[d].w), nd), st[k].g[d]);
-        }
+        for (int d = 0; d < D; ++d) { st[k].g[d].x *= sc; st[k].g[d].y *= sc; }
+      }
+      st[k].mref = vm;
+      st[k].nm = make_float2(-vm, -vm);
+      const float2 p0 = make_float2(ex2_approx(v0.x - vm), ex2_approx(v0.y - vm));
+      const float2 p1 = make_float2(ex2_approx(v1.x - vm), ex2_approx(v1.y - vm));
+      ps[k] = __fadd2_rn(p0, p1);
+      if (GRAD) { p0s[k] = p0; p1s[k] = p1; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    st[k].s = __fadd2_rn(st[k].s, ps[k]);
+    if (GRAD) {  // sum_j e_ij (p_j - p_i): differences recomputed (last round only) to keep registers flat in D
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float2 nd = make_float2(st[k].nx[d], st[k].nx[d]);
+        st[k].g[d] = __ffma2_rn(p0s[k], __fadd2_rn(make_float2(X[d].x, X[d].y), nd), st[k].g[d]);
+        st[k].g[d] = __ffma2_rn(p1s[k], __fadd2_rn(make_float2(X[d].z, X[d].w), nd), st[k].g[d]);
       }
     }
+  }
+}
+
+// Column tile staged per warp in shared memory with cp.async (L2 -> smem, no registers, no L1): T columns of the D
+// coordinate arrays plus the soft-min offsets, double buffered, so the loads of tile t+1 are in flight during the
+// whole evaluation of tile t (thousands of cycles: the L2 latency is fully hidden).
+template <int D>
+__host__ __device__ constexpr int stream_tile_cols() { return D <= 4 ? 128 : (D <= 8 ? 64 : 32); }
+template <int D>
+__host__ __device__ constexpr int stream_warp_smem_floats() { return 2 * (D + 1) * stream_tile_cols<D>(); }
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// R rows of this lane against columns [0, ncols) of one column set (ncols multiple of 4; SoA global arrays
+// pts[d][strideP], ch[]).  The h arrays are rewritten every round by other SMs: cp.async.cg reads them from L2.
+template <int D, int R, bool GRAD>
+__device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const float* __restrict__ pts, int strideP,
+                                            const float* ch, int ncols, float coef, float* wsm, int lane) {
+  constexpr int T = stream_tile_cols<D>();
+  const float2 coef2 = make_float2(coef, coef);
+  const float big = exp2f(kTauS);
+  const int ntiles = (ncols + T - 1) / T;
+  auto issue = [&](int t) {
+    const int c = t * T + lane * 4;
+    if (lane * 4 < T && c < ncols) {
+      float* dst = wsm + (t & 1) * (D + 1) * T + lane * 4;
+#pragma unroll
+      for (int d = 0; d < D; ++d) cp_async16(dst + d * T, pts + (size_t)d * strideP + c);
+      cp_async16(dst + D * T, ch + c);
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  for (int t = 0; t < ntiles; ++t) {
+    if (t + 1 < ntiles) issue(t + 1); else cp_async_commit();  // keep one group per iteration
+    cp_async_wait1();
+    __syncwarp();
+    const float* tb = wsm + (t & 1) * (D + 1) * T;
+    const int n = min(T, ncols - t * T);
+#pragma unroll 1
+    for (int j = 0; j < n; j += 4) {
+      float4 X[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) X[d] = *reinterpret_cast<const float4*>(tb + d * T + j);
+      const float4 H = *reinterpret_cast<const float4*>(tb + D * T + j);
+      stream_chunk<D, R, GRAD>(st, X, H, coef2, big);
+    }
+    __syncwarp();  // every lane is done with this buffer before tile t+2 overwrites it
   }
 }
 
@@ -120,7 +184,6 @@ __device__ __forceinline__ void urow_reset(URow<D, R, GRAD> (&st)[R]) {
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     st[k].mref = kNegBig;
-    st[k].thr = kNegBig;
     st[k].nm = make_float2(-kNegBig, -kNegBig);
     st[k].s = make_float2(0.f, 0.f);
 #pragma unroll
@@ -133,6 +196,103 @@ __device__ __forceinline__ long long cell_index(const SinkhornParams& b, bool st
                  : (long long)cell * b.s_cell_m + (long long)slot * b.s_slot_m;
 }
 
+// One warp unit: rows [blk*32R, blk*32R + 32R) of one cloud of problem `prob` against one column set, round r.
+template <int D, int R>
+__device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int prob, int uu, int lane, float* wsm) {
+  const SinkhornParams& b = p.b;
+  const int B = b.B, strideP = p.strideP;
+  const int img = prob / B, slot = prob - img * B;
+  const int nrounds = b.sched_rounds[img];
+  if (r >= nrounds) return;  // image finished (or skipped)
+  const bool last = r == nrounds - 1;
+  const int cur = r & 1;
+  const int N = b.cu_n[img + 1] - b.cu_n[img], M = b.cu_m[img + 1] - b.cu_m[img];
+  const int Nq = (N + 3) & ~3, Mq = (M + 3) & ~3;
+  const bool rows_x = uu < 2 * p.nbx;
+  const int ub = rows_x ? uu : uu - 2 * p.nbx;
+  const int blk = ub >> 1;
+  const bool own = (ub & 1) == 0;
+  const int rcount = rows_x ? N : M;
+  if (blk * 32 * R >= rcount) return;  // padded unit of a smaller image
+  const int rbase = rows_x ? 0 : p.nqMax;
+  const RoundConst rc = b.sched[(size_t)img * KDOT_MAX_ROUNDS + r];
+  const double rho = b.rho;
+  const float* pts = p.pts + (size_t)prob * D * strideP;
+  const float* lw2 = p.lw2 + (size_t)prob * strideP;
+  float* potS = p.pot + (size_t)prob * 2 * strideP;
+  float* potC = potS + strideP;
+  const float* hSc = p.h + ((size_t)prob * 4 + cur * 2) * strideP;
+  const float* hCc = hSc + strideP;
+  float* hSn = p.h + ((size_t)prob * 4 + (cur ^ 1) * 2) * strideP;
+  float* hCn = hSn + strideP;
+
+  if (last && rows_x) {
+    if (!own) return;  // the student's last round is done by the "own" unit for both column sets
+    // one row per pass keeps the gradient accumulators in registers for every D
+    for (int k0 = 0; k0 < R; ++k0) {
+      const int i = blk * 32 * R + lane + 32 * k0;
+      const bool act = i < N;
+      const int src = act ? i : 0;
+      URow<D, 1, true> st[1];
+      urow_reset<D, 1, true>(st);
+#pragma unroll
+      for (int d = 0; d < D; ++d) st[0].nx[d] = -pts[(size_t)d * strideP + src];
+      stream_rows<D, 1, true>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane);
+      const float sS = st[0].s.x + st[0].s.y;
+      const float S = rc.scale * (st[0].mref + lg2_approx(sS));
+      float gS[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) gS[d] = (st[0].g[d].x + st[0].g[d].y) / sS;
+      urow_reset<D, 1, true>(st);
+      stream_rows<D, 1, true>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane);
+      if (!act) continue;
+      const float sC = st[0].s.x + st[0].s.y;
+      const float C = rc.scale * (st[0].mref + lg2_approx(sC));
+      const RowFinal f = row_final(S, C, rho, rc.eps);
+      const float lam = rho < 0.0 ? 1.f : (float)(1.0 / (1.0 + (double)rc.eps / rho));
+      const float gfac = rho < 0.0 ? 1.f : (float)((rho + 0.5 * (double)rc.eps) / rho) * lam;
+      const long long g = cell_index(b, true, b.cu_n[img] + i, slot);
+      const float wg = b.ws ? b.ws[g] : __fdiv_rn(1.0f, (float)N);
+      p.term[(size_t)prob * strideP + i] = wg * f.term;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        float gv = wg * gfac * (f.eS * gS[d] - f.eC * ((st[0].g[d].x + st[0].g[d].y) / sC));
+        if (b.normalize && D == 2) gv = __fdiv_rn(gv, d == 0 ? b.w : b.h);
+        b.grad_xs[(size_t)D * g + d] = gv;
+      }
+      if (b.grad_ws) b.grad_ws[g] = f.term;
+    }
+    return;
+  }
+
+  const bool cols_x = (rows_x == own);
+  const float* cpts = cols_x ? pts : pts + p.nqMax;
+  const float* ch = (own ? hSc : hCc) + (cols_x ? 0 : p.nqMax);
+  const int ncols = cols_x ? Nq : Mq;
+  URow<D, R, false> st[R];
+  urow_reset<D, R, false>(st);
+  int ridx[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int i = blk * 32 * R + lane + 32 * k;
+    ridx[k] = i < rcount ? rbase + i : -1;
+    const int src = ridx[k] >= 0 ? ridx[k] : rbase;
+#pragma unroll
+    for (int d = 0; d < D; ++d) st[k].nx[d] = -pts[(size_t)d * strideP + src];
+  }
+  stream_rows<D, R, false>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane);
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    if (ridx[k] < 0) continue;
+    const float lse = st[k].mref + lg2_approx(st[k].s.x + st[k].s.y);
+    float* pot = own ? potS : potC;
+    const float nv = rc.scale * lse;
+    const float pv = (r == 0 || last) ? nv : 0.5f * (__ldcg(pot + ridx[k]) + nv);
+    pot[ridx[k]] = pv;
+    if (!last) (own ? hSn : hCn)[ridx[k]] = fmaf(pv, rc.hmul, __ldcg(lw2 + ridx[k]));
+  }
+}
+
 template <int D, int R>
 __global__ void __launch_bounds__(kStreamThreads, 2) kdot_stream_kernel(StreamParams p) {
   cg::grid_group grid = cg::this_grid();
@@ -141,6 +301,8 @@ __global__ void __launch_bounds__(kStreamThreads, 2) kdot_stream_kernel(StreamPa
   const int nprob = b.nimg * B;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int strideP = p.strideP;
+  extern __shared__ __align__(16) float s_tiles[];  // per warp: 2 x (D+1) x T floats (cp.async column tiles)
+  float* wsm = s_tiles + (size_t)warp * stream_warp_smem_floats<D>();
   __shared__ float s_box[kStreamThreads / 32][2 * D];
   __shared__ int s_info[2];
   __shared__ ImgSched s_is;
@@ -225,6 +387,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) kdot_stream_kernel(StreamPa
     __syncthreads();
   }
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < KDOT_MAX_ROUNDS; r += gridDim.x * blockDim.x) p.ctr[r] = 0u;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nprob; q += gridDim.x * blockDim.x) p.done[q] = 0u;
   grid.sync();
 
   // ---------------- phase 0b: stage problems (SoA, padded) ----------------
@@ -266,110 +429,41 @@ __global__ void __launch_bounds__(kStreamThreads, 2) kdot_stream_kernel(StreamPa
   }
   grid.sync();
 
-  // ---------------- rounds ----------------
-  const int gwarp = blockIdx.x * nwarps + warp;
-  (void)gwarp;
-  const long long units_total = (long long)nprob * p.upp;
-  const double rho = b.rho;
-  for (int r = 0; r < max_rounds; ++r) {
-    const int cur = r & 1;
-    for (;;) {
-      unsigned int u = 0;
-      if (lane == 0) u = atomicAdd(&p.ctr[r], 1u);
-      u = __shfl_sync(0xffffffffu, u, 0);
-      if ((long long)u >= units_total) break;
-      const int prob = (int)(u / p.upp), uu = (int)(u - (unsigned)prob * p.upp);
-      const int img = prob / B, slot = prob - img * B;
-      const int nrounds = b.sched_rounds[img];
-      if (r >= nrounds) continue;  // image finished (or skipped)
-      const bool last = r == nrounds - 1;
-      const int N = b.cu_n[img + 1] - b.cu_n[img], M = b.cu_m[img + 1] - b.cu_m[img];
-      const int Nq = (N + 3) & ~3, Mq = (M + 3) & ~3;
-      const bool rows_x = uu < 2 * p.nbx;
-      const int ub = rows_x ? uu : uu - 2 * p.nbx;
-      const int blk = ub >> 1;
-      const bool own = (ub & 1) == 0;
-      const int rcount = rows_x ? N : M;
-      if (blk * 32 * R >= rcount) continue;  // padded unit of a smaller image
-      const int rbase = rows_x ? 0 : p.nqMax;
-      const RoundConst rc = b.sched[(size_t)img * KDOT_MAX_ROUNDS + r];
-      const float* pts = p.pts + (size_t)prob * D * strideP;
-      const float* lw2 = p.lw2 + (size_t)prob * strideP;
-      float* potS = p.pot + (size_t)prob * 2 * strideP;
-      float* potC = potS + strideP;
-      const float* hSc = p.h + ((size_t)prob * 4 + cur * 2) * strideP;
-      const float* hCc = hSc + strideP;
-      float* hSn = p.h + ((size_t)prob * 4 + (cur ^ 1) * 2) * strideP;
-      float* hCn = hSn + strideP;
-
-      if (last && rows_x) {
-        if (!own) continue;  // the student's last round is done by the "own" unit for both column sets
-        // one row per pass keeps the gradient accumulators in registers for every D
-        for (int k0 = 0; k0 < R; ++k0) {
-          const int i = blk * 32 * R + lane + 32 * k0;
-          const bool act = i < N;
-          const int src = act ? i : 0;
-          URow<D, 1, true> st[1];
-          urow_reset<D, 1, true>(st);
-#pragma unroll
-          for (int d = 0; d < D; ++d) st[0].nx[d] = -pts[(size_t)d * strideP + src];
-          stream_rows<D, 1, true>(st, pts, strideP, hSc, 0, Nq, rc.coef);
-          const float sS = st[0].s.x + st[0].s.y;
-          const float S = rc.scale * (st[0].mref + lg2_approx(sS));
-          float gS[D];
-#pragma unroll
-          for (int d = 0; d < D; ++d) gS[d] = (st[0].g[d].x + st[0].g[d].y) / sS;
-          urow_reset<D, 1, true>(st);
-          stream_rows<D, 1, true>(st, pts + p.nqMax, strideP, hCc + p.nqMax, 0, Mq, rc.coef);
-          if (!act) continue;
-          const float sC = st[0].s.x + st[0].s.y;
-          const float C = rc.scale * (st[0].mref + lg2_approx(sC));
-          const RowFinal f = row_final(S, C, rho, rc.eps);
-          const float lam = rho < 0.0 ? 1.f : (float)(1.0 / (1.0 + (double)rc.eps / rho));
-          const float gfac = rho < 0.0 ? 1.f : (float)((rho + 0.5 * (double)rc.eps) / rho) * lam;
-          const long long g = cell_index(b, true, b.cu_n[img] + i, slot);
-          const float wg = b.ws ? b.ws[g] : __fdiv_rn(1.0f, (float)N);
-          p.term[(size_t)prob * strideP + i] = wg * f.term;
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            float gv = wg * gfac * (f.eS * gS[d] - f.eC * ((st[0].g[d].x + st[0].g[d].y) / sC));
-            if (b.normalize && D == 2) gv = __fdiv_rn(gv, d == 0 ? b.w : b.h);
-            b.grad_xs[(size_t)D * g + d] = gv;
-          }
-          if (b.grad_ws) b.grad_ws[g] = f.term;
+  // ---------------- rounds: dataflow over a single global FIFO of warp units ----------------
+  // Unit ids enumerate (round, problem, unit-in-problem) in that order.  A unit of round r may start once all units
+  // of round r-1 of ITS problem have finished (done[prob] == r * upp); because ids are handed out in FIFO order and
+  // the whole grid is co-resident (cooperative launch), the units it waits for are already running, so there is no
+  // deadlock -- and with more than a few problems in the batch the previous round of a problem finished long ago,
+  // so nobody actually waits and there is no global barrier between rounds.
+  const long long upr = (long long)nprob * p.upp;
+  const unsigned long long total_ids = (unsigned long long)max_rounds * (unsigned long long)upr;
+  unsigned long long* fifo = reinterpret_cast<unsigned long long*>(p.ctr);
+  for (;;) {
+    unsigned long long id = 0;
+    if (lane == 0) id = atomicAdd(fifo, 1ull);
+    id = __shfl_sync(0xffffffffu, id, 0);
+    if (id >= total_ids) break;
+    const int r = (int)(id / (unsigned long long)upr);
+    const long long u = (long long)(id - (unsigned long long)r * (unsigned long long)upr);
+    const int prob = (int)(u / p.upp), uu = (int)(u - (long long)prob * p.upp);
+    if (r > 0) {
+      if (lane == 0) {
+        const unsigned int need = (unsigned int)r * (unsigned int)p.upp;
+        unsigned int seen;
+        for (;;) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.done + prob) : "memory");
+          if (seen >= need) break;
+          __nanosleep(100);
         }
-        continue;
       }
-
-      const bool cols_x = (rows_x == own);
-      const float* cpts = cols_x ? pts : pts + p.nqMax;
-      const float* ch = (own ? hSc : hCc) + (cols_x ? 0 : p.nqMax);
-      const int ncols = cols_x ? Nq : Mq;
-      URow<D, R, false> st[R];
-      urow_reset<D, R, false>(st);
-      int ridx[R];
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        const int i = blk * 32 * R + lane + 32 * k;
-        ridx[k] = i < rcount ? rbase + i : -1;
-        const int src = ridx[k] >= 0 ? ridx[k] : rbase;
-#pragma unroll
-        for (int d = 0; d < D; ++d) st[k].nx[d] = -pts[(size_t)d * strideP + src];
-      }
-      stream_rows<D, R, false>(st, cpts, strideP, ch, 0, ncols, rc.coef);
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        if (ridx[k] < 0) continue;
-        const float lse = st[k].mref + lg2_approx(st[k].s.x + st[k].s.y);
-        float* pot = own ? potS : potC;
-        const float nv = rc.scale * lse;
-        const float pv = (r == 0 || last) ? nv : 0.5f * (pot[ridx[k]] + nv);
-        pot[ridx[k]] = pv;
-        if (!last) (own ? hSn : hCn)[ridx[k]] = fmaf(pv, rc.hmul, lw2[ridx[k]]);
-      }
+      __syncwarp();
     }
-    grid.sync();
+    stream_unit<D, R>(p, r, prob, uu, lane, wsm);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(p.done + prob, 1u);
   }
+  grid.sync();
 
   // ---------------- final: fixed-order loss reduction, one warp per image ----------------
   for (int img = blockIdx.x * nwarps + warp; img < b.nimg; img += gridDim.x * nwarps) {
@@ -384,9 +478,9 @@ __global__ void __launch_bounds__(kStreamThreads, 2) kdot_stream_kernel(StreamPa
       const float* potS = p.pot + (size_t)prob * 2 * strideP;
       const float* potC = potS + strideP;
       double acc = 0.0;
-      for (int i = lane; i < N; i += 32) acc += (double)term[i];
+      for (int i = lane; i < N; i += 32) acc += (double)__ldcg(term + i);
       for (int j = lane; j < M; j += 32) {
-        const RowFinal f = row_final(potS[p.nqMax + j], potC[p.nqMax + j], rho, eps_last);
+        const RowFinal f = row_final(__ldcg(potS + p.nqMax + j), __ldcg(potC + p.nqMax + j), b.rho, eps_last);
         const long long g = cell_index(b, false, b.cu_m[img] + j, slot);
         const float wg = b.wt ? b.wt[g] : __fdiv_rn(1.0f, (float)M);
         acc += (double)wg * (double)f.term;
@@ -401,7 +495,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) kdot_stream_kernel(StreamPa
 
 struct StreamPlan {
   int strideP, nqMax, nbx, nby, upp, R;
-  size_t off_pts, off_lw, off_pot, off_h, off_term, off_ctr, off_sched, off_rounds, total;
+  size_t off_pts, off_lw, off_pot, off_h, off_term, off_ctr, off_done, off_sched, off_rounds, total;
 };
 
 static int rows_per_lane(int D) { return D <= 2 ? 4 : (D <= 8 ? 2 : 1); }
@@ -424,6 +518,7 @@ StreamPlan plan_stream(int nimg, int max_n, int max_m, int B, int D) {
   s.off_h = o;      o = up(o + nprob * 4 * P * 4);
   s.off_term = o;   o = up(o + nprob * P * 4);
   s.off_ctr = o;    o = up(o + (size_t)KDOT_MAX_ROUNDS * 4);
+  s.off_done = o;   o = up(o + nprob * 4);
   s.off_sched = o;  o = up(o + (size_t)nimg * KDOT_MAX_ROUNDS * sizeof(RoundConst));
   s.off_rounds = o; o = up(o + (size_t)nimg * 4);
   s.total = o;
@@ -443,13 +538,14 @@ static cudaError_t launch_stream_t(StreamParams& sp, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kdot_stream_kernel<D, R>, kStreamThreads, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kdot_stream_kernel<D, R>, kStreamThreads,
+                                                                  (kStreamThreads / 32) * stream_warp_smem_floats<D>() * sizeof(float));
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) return cudaErrorLaunchOutOfResources;
   }
   void* args[] = {&sp};
   return cudaLaunchCooperativeKernel((const void*)kdot_stream_kernel<D, R>, dim3(blocks_per_sm * sms), dim3(kStreamThreads),
-                                     args, 0, stream);
+                                     args, (kStreamThreads / 32) * stream_warp_smem_floats<D>() * sizeof(float), stream);
 }
 
 cudaError_t launch_stream(const SinkhornParams& prm, int D, int max_n, int max_m, void* workspace, cudaStream_t stream) {
@@ -467,6 +563,7 @@ cudaError_t launch_stream(const SinkhornParams& prm, int D, int max_n, int max_m
   sp.h = (float*)(base + pl.off_h);
   sp.term = (float*)(base + pl.off_term);
   sp.ctr = (unsigned int*)(base + pl.off_ctr);
+  sp.done = (unsigned int*)(base + pl.off_done);
   switch (D) {
     case 1: return launch_stream_t<1, 2>(sp, stream);
     case 2: return launch_stream_t<2, 4>(sp, stream);

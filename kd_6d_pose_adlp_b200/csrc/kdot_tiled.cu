@@ -16,8 +16,17 @@
 
 namespace kdot {
 
-constexpr int kTiledThreads = 256;
-constexpr int kRows = 4;                     // rows per lane
+#ifndef KDOT_TILED_THREADS
+#define KDOT_TILED_THREADS 256
+#endif
+#ifndef KDOT_TILED_ROWS
+#define KDOT_TILED_ROWS 4
+#endif
+#ifndef KDOT_TILED_MINBLOCKS
+#define KDOT_TILED_MINBLOCKS 2
+#endif
+constexpr int kTiledThreads = KDOT_TILED_THREADS;
+constexpr int kRows = KDOT_TILED_ROWS;       // rows per lane
 constexpr int kUnitRows = 32 * kRows;        // rows per warp unit
 constexpr float kTau = 24.f;                 // lazy-rescale threshold (log2 units)
 
@@ -113,66 +122,85 @@ template <bool kGrad>
 struct RowState {
   float2 nx, ny;    // (-px, -px), (-py, -py)
   float2 nm;        // (-mref, -mref)
-  float mref;       // reference exponent of the running sums (stale by at most kTau)
-  float thr;        // mref + kTau: a larger value triggers a re-base
+  float mref;       // reference exponent of the running sums (may be stale by up to ~kTau)
   float2 s;         // two partial exp sums
   float2 gx, gy;    // sum e * (p_j - p_i), two partials each   (kGrad only)
 };
 
+// The running sums of a row are kept relative to a reference exponent `mref` that may be STALE: instead of tracking
+// the exact running max (one FMNMX per pair plus compares), the hot loop just evaluates p = 2^(v - mref) and
+// looks at the chunk's partial sum.  If it exceeds 2^kTau (in particular +inf: the very first chunk, where
+// mref = -big) some v is more than ~kTau above the reference; only then the cold path recomputes that row's chunk
+// with the exact max and re-bases the sums.  Values far BELOW the reference need no care (they underflow to the
+// correct negligible contribution).  Hot path per 4 pairs: 4 FADD2 + 2 FMUL2 + 4 FFMA2 + 2 FADD2 + 4 MUFU + 2 FADD2
+// + FADD + FSETP = 5.0 issue slots per pair against the SFU's 8 cycles per warp-wide ex2.
 template <bool kGrad>
 __device__ __forceinline__ void rows_vs_columns(RowState<kGrad> (&st)[kRows], const float* __restrict__ cx,
                                                 const float* __restrict__ cy, const float* __restrict__ ch, int c0,
                                                 int c1, float coef) {
   const float2 coef2 = make_float2(coef, coef);
+  const float big = exp2f(kTau);
 #pragma unroll 1
   for (int j = c0; j < c1; j += 4) {
     const float4 X = *reinterpret_cast<const float4*>(cx + j);
     const float4 Y = *reinterpret_cast<const float4*>(cy + j);
     const float4 H = *reinterpret_cast<const float4*>(ch + j);
-    float2 v0[kRows], v1[kRows], d0[kRows], d1[kRows], e0[kRows], e1[kRows];
+    float2 ps[kRows], pgx[kRows], pgy[kRows];
     bool rebase = false;
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {
-      d0[k] = __fadd2_rn(make_float2(X.x, X.y), st[k].nx);
-      d1[k] = __fadd2_rn(make_float2(X.z, X.w), st[k].nx);
-      e0[k] = __fadd2_rn(make_float2(Y.x, Y.y), st[k].ny);
-      e1[k] = __fadd2_rn(make_float2(Y.z, Y.w), st[k].ny);
-      const float2 q0 = __ffma2_rn(e0[k], e0[k], __fmul2_rn(d0[k], d0[k]));
-      const float2 q1 = __ffma2_rn(e1[k], e1[k], __fmul2_rn(d1[k], d1[k]));
-      v0[k] = __ffma2_rn(q0, coef2, make_float2(H.x, H.y));
-      v1[k] = __ffma2_rn(q1, coef2, make_float2(H.z, H.w));
-      const float vm = fmaxf(fmaxf(v0[k].x, v0[k].y), fmaxf(v1[k].x, v1[k].y));
-      rebase |= vm > st[k].thr;
+      const float2 d0 = __fadd2_rn(make_float2(X.x, X.y), st[k].nx);
+      const float2 d1 = __fadd2_rn(make_float2(X.z, X.w), st[k].nx);
+      const float2 e0 = __fadd2_rn(make_float2(Y.x, Y.y), st[k].ny);
+      const float2 e1 = __fadd2_rn(make_float2(Y.z, Y.w), st[k].ny);
+      const float2 q0 = __ffma2_rn(e0, e0, __fmul2_rn(d0, d0));
+      const float2 q1 = __ffma2_rn(e1, e1, __fmul2_rn(d1, d1));
+      // v - mref with the subtraction folded into the per-row offset hm = (H - mref) would cost the same FADD2
+      const float2 a0 = __fadd2_rn(__ffma2_rn(q0, coef2, make_float2(H.x, H.y)), st[k].nm);
+      const float2 a1 = __fadd2_rn(__ffma2_rn(q1, coef2, make_float2(H.z, H.w)), st[k].nm);
+      const float2 p0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
+      const float2 p1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+      ps[k] = __fadd2_rn(p0, p1);
+      if (kGrad) {
+        pgx[k] = __ffma2_rn(p1, d1, __fmul2_rn(p0, d0));
+        pgy[k] = __ffma2_rn(p1, e1, __fmul2_rn(p0, e0));
+      }
+      rebase |= !(ps[k].x + ps[k].y <= big);
     }
-    if (rebase) {  // cold: some row met a value more than kTau above its reference -> re-base its running sums
+    if (rebase) {  // cold: recompute the offending rows' chunk against its exact max and re-base their sums
 #pragma unroll
       for (int k = 0; k < kRows; ++k) {
-        const float vm = fmaxf(fmaxf(v0[k].x, v0[k].y), fmaxf(v1[k].x, v1[k].y));
-        if (vm > st[k].thr) {
-          const float sc = ex2_approx(st[k].mref - vm);
-          st[k].s.x *= sc; st[k].s.y *= sc;
-          if (kGrad) {
-            st[k].gx.x *= sc; st[k].gx.y *= sc;
-            st[k].gy.x *= sc; st[k].gy.y *= sc;
-          }
-          st[k].mref = vm;
-          st[k].thr = vm + kTau;
-          st[k].nm = make_float2(-vm, -vm);
+        if (ps[k].x + ps[k].y <= big) continue;
+        const float2 d0 = __fadd2_rn(make_float2(X.x, X.y), st[k].nx);
+        const float2 d1 = __fadd2_rn(make_float2(X.z, X.w), st[k].nx);
+        const float2 e0 = __fadd2_rn(make_float2(Y.x, Y.y), st[k].ny);
+        const float2 e1 = __fadd2_rn(make_float2(Y.z, Y.w), st[k].ny);
+        const float2 v0 = __ffma2_rn(__ffma2_rn(e0, e0, __fmul2_rn(d0, d0)), coef2, make_float2(H.x, H.y));
+        const float2 v1 = __ffma2_rn(__ffma2_rn(e1, e1, __fmul2_rn(d1, d1)), coef2, make_float2(H.z, H.w));
+        const float vm = fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y));
+        const float sc = ex2_approx(st[k].mref - vm);  // 0 for the first chunk (mref = -big)
+        st[k].s.x *= sc; st[k].s.y *= sc;
+        if (kGrad) {
+          st[k].gx.x *= sc; st[k].gx.y *= sc;
+          st[k].gy.x *= sc; st[k].gy.y *= sc;
+        }
+        st[k].mref = vm;
+        st[k].nm = make_float2(-vm, -vm);
+        const float2 p0 = make_float2(ex2_approx(v0.x - vm), ex2_approx(v0.y - vm));
+        const float2 p1 = make_float2(ex2_approx(v1.x - vm), ex2_approx(v1.y - vm));
+        ps[k] = __fadd2_rn(p0, p1);
+        if (kGrad) {
+          pgx[k] = __ffma2_rn(p1, d1, __fmul2_rn(p0, d0));
+          pgy[k] = __ffma2_rn(p1, e1, __fmul2_rn(p0, e0));
         }
       }
     }
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {
-      const float2 a0 = __fadd2_rn(v0[k], st[k].nm);
-      const float2 a1 = __fadd2_rn(v1[k], st[k].nm);
-      const float2 p0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
-      const float2 p1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
-      st[k].s = __fadd2_rn(st[k].s, __fadd2_rn(p0, p1));
+      st[k].s = __fadd2_rn(st[k].s, ps[k]);
       if (kGrad) {
-        st[k].gx = __ffma2_rn(p0, d0[k], st[k].gx);
-        st[k].gx = __ffma2_rn(p1, d1[k], st[k].gx);
-        st[k].gy = __ffma2_rn(p0, e0[k], st[k].gy);
-        st[k].gy = __ffma2_rn(p1, e1[k], st[k].gy);
+        st[k].gx = __fadd2_rn(st[k].gx, pgx[k]);
+        st[k].gy = __fadd2_rn(st[k].gy, pgy[k]);
       }
     }
   }
@@ -183,7 +211,6 @@ __device__ __forceinline__ void rows_reset(RowState<kGrad> (&st)[kRows]) {
 #pragma unroll
   for (int k = 0; k < kRows; ++k) {
     st[k].mref = kNegBig;
-    st[k].thr = kNegBig;
     st[k].nm = make_float2(-kNegBig, -kNegBig);
     st[k].s = make_float2(0.f, 0.f);
     st[k].gx = make_float2(0.f, 0.f);
@@ -194,7 +221,7 @@ __device__ __forceinline__ void rows_reset(RowState<kGrad> (&st)[kRows]) {
 // ---------------------------------------------------------------------------------------------------------
 // main kernel: one CTA per (image, slot)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTiledThreads, 2) kdot_tiled_kernel(SinkhornParams prm) {
+__global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tiled_kernel(SinkhornParams prm) {
   const int B = prm.B;
   const int img = blockIdx.x / B, slot = blockIdx.x - img * B;
   const int nrounds = prm.sched_rounds[img];

@@ -135,9 +135,10 @@ def test_bad_arguments_fail_loudly():
         ot_loss_batched(t["xs"], t["ws"], t["xt"], t["wt"], b["pos_per_img"][:-1] + [999], b["pos_per_img_t"])
 
 
-def test_stream_kernel_matches_oracle_d2(monkeypatch):
-    """The cooperative streaming kernel on the same D = 2 problems as the tiled kernel (forced path)."""
-    monkeypatch.setenv("KDOT_FORCE_PATH", "stream")
+@pytest.mark.parametrize("path", ["stream", "tiled"])
+def test_large_path_kernels_match_oracle_d2(path, monkeypatch):
+    """Both large-cloud kernels (streaming cooperative = default, tiled = KDOT_FORCE_PATH=tiled) on D = 2 problems."""
+    monkeypatch.setenv("KDOT_FORCE_PATH", path)
     check(ot_batch(3, seed=7, n_range=(40, 90), m_range=(50, 120), p_empty_teacher=0.0))
     check(ot_batch(6, seed=9, n_range=(1, 70), m_range=(1, 70), p_empty_teacher=0.3))
     check(ot_batch(4, seed=31, n_range=(33, 40), m_range=(33, 40)), reach=None, scaling=0.7)
