@@ -46,8 +46,8 @@ struct StreamParams {
 template <int D, int R, bool GRAD>
 struct URow {
   float nx[D];          // -p_i
-  float mref;
-  float2 nm;
+  float mref;           // reference exponent of the running sums (may be stale by up to ~kTauS)
+  float2 mu;            // mref / (-coef), duplicated: folded into the squared-distance FMA chain
   float2 s;
   float2 g[GRAD ? D : 1];
 };
@@ -58,31 +58,43 @@ __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinter
 // Running sums are kept relative to a possibly stale reference exponent mref; a chunk whose partial sum exceeds
 // 2^kTauS (or is +inf: first chunk, mref = -big) takes the cold path that re-bases on the exact max (see
 // kdot_tiled.cu for the full argument).
-template <int D, int R, bool GRAD>
+// Hot-path arithmetic per pair: the reference exponent is folded into the first FMA of the squared distance,
+//   a = v - mref = coef * (mu + dx^2 + dy^2 + ...) + h   with   mu = mref / (-coef)   (row constant),
+// so a pair costs D FADD + D FFMA (distance) + 1 FFMA (scale + offset): no separate subtraction of the reference.
+// A rounding error in mu shifts every exponent of the row by the same amount and cancels in the soft-min.
+// FOLD is used only while the exponents are small (early, warm rounds: eps >= eps_0 / 256, |h| < ~200): there the
+// two extra roundings it introduces are < 2e-5.  In the cold rounds (|h| ~ 1e3..1e4) the unfolded form
+// (one rounding of v, then an exact subtraction) is kept, because those rounds set the accuracy of the result.
+template <int D, int R, bool GRAD, bool FOLD>
 __device__ __forceinline__ void stream_chunk(URow<D, R, GRAD> (&st)[R], const float4 (&X)[D], const float4& H,
-                                             const float2 coef2, const float big) {
+                                             const float2 coef2, const float inv_ncoef, const float big) {
   float2 ps[R], p0s[GRAD ? R : 1], p1s[GRAD ? R : 1];
   bool rebase = false;
 #pragma unroll
   for (int k = 0; k < R; ++k) {
-    float2 q0 = make_float2(0.f, 0.f), q1 = q0;
+    float2 q0 = st[k].mu, q1 = st[k].mu;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       const float2 nd = make_float2(st[k].nx[d], st[k].nx[d]);
       const float2 a0 = __fadd2_rn(make_float2(X[d].x, X[d].y), nd);
       const float2 a1 = __fadd2_rn(make_float2(X[d].z, X[d].w), nd);
-      q0 = d == 0 ? __fmul2_rn(a0, a0) : __ffma2_rn(a0, a0, q0);
-      q1 = d == 0 ? __fmul2_rn(a1, a1) : __ffma2_rn(a1, a1, q1);
+      q0 = (!FOLD && d == 0) ? __fmul2_rn(a0, a0) : __ffma2_rn(a0, a0, q0);
+      q1 = (!FOLD && d == 0) ? __fmul2_rn(a1, a1) : __ffma2_rn(a1, a1, q1);
     }
-    const float2 e0 = __fadd2_rn(__ffma2_rn(q0, coef2, make_float2(H.x, H.y)), st[k].nm);
-    const float2 e1 = __fadd2_rn(__ffma2_rn(q1, coef2, make_float2(H.z, H.w)), st[k].nm);
+    float2 e0 = __ffma2_rn(q0, coef2, make_float2(H.x, H.y));
+    float2 e1 = __ffma2_rn(q1, coef2, make_float2(H.z, H.w));
+    if (!FOLD) {
+      const float2 nm = make_float2(-st[k].mref, -st[k].mref);
+      e0 = __fadd2_rn(e0, nm);
+      e1 = __fadd2_rn(e1, nm);
+    }
     const float2 p0 = make_float2(ex2_approx(e0.x), ex2_approx(e0.y));
     const float2 p1 = make_float2(ex2_approx(e1.x), ex2_approx(e1.y));
     ps[k] = __fadd2_rn(p0, p1);
     if (GRAD) { p0s[k] = p0; p1s[k] = p1; }
     rebase |= !(ps[k].x + ps[k].y <= big);
   }
-  if (rebase) {
+  if (rebase) {  // cold: exact max of the offending rows' chunk, re-base their running sums
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       if (ps[k].x + ps[k].y <= big) continue;
@@ -98,14 +110,15 @@ __device__ __forceinline__ void stream_chunk(URow<D, R, GRAD> (&st)[R], const fl
       const float2 v0 = __ffma2_rn(q0, coef2, make_float2(H.x, H.y));
       const float2 v1 = __ffma2_rn(q1, coef2, make_float2(H.z, H.w));
       const float vm = fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y));
-      const float sc = ex2_approx(st[k].mref - vm);
+      const float sc = ex2_approx(st[k].mref - vm);  // 0 for the first chunk (mref = -big)
       st[k].s.x *= sc; st[k].s.y *= sc;
       if (GRAD) {
 #pragma unroll
         for (int d = 0; d < D; ++d) { st[k].g[d].x *= sc; st[k].g[d].y *= sc; }
       }
       st[k].mref = vm;
-      st[k].nm = make_float2(-vm, -vm);
+      const float mu = vm * inv_ncoef;
+      st[k].mu = make_float2(mu, mu);
       const float2 p0 = make_float2(ex2_approx(v0.x - vm), ex2_approx(v0.y - vm));
       const float2 p1 = make_float2(ex2_approx(v1.x - vm), ex2_approx(v1.y - vm));
       ps[k] = __fadd2_rn(p0, p1);
@@ -143,11 +156,12 @@ __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_g
 
 // R rows of this lane against columns [0, ncols) of one column set (ncols multiple of 4; SoA global arrays
 // pts[d][strideP], ch[]).  The h arrays are rewritten every round by other SMs: cp.async.cg reads them from L2.
-template <int D, int R, bool GRAD>
+template <int D, int R, bool GRAD, bool FOLD>
 __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const float* __restrict__ pts, int strideP,
                                             const float* ch, int ncols, float coef, float* wsm, int lane) {
   constexpr int T = stream_tile_cols<D>();
   const float2 coef2 = make_float2(coef, coef);
+  const float inv_ncoef = -1.0f / coef;
   const float big = exp2f(kTauS);
   const int ntiles = (ncols + T - 1) / T;
   auto issue = [&](int t) {
@@ -173,18 +187,18 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
 #pragma unroll
       for (int d = 0; d < D; ++d) X[d] = *reinterpret_cast<const float4*>(tb + d * T + j);
       const float4 H = *reinterpret_cast<const float4*>(tb + D * T + j);
-      stream_chunk<D, R, GRAD>(st, X, H, coef2, big);
+      stream_chunk<D, R, GRAD, FOLD>(st, X, H, coef2, inv_ncoef, big);
     }
     __syncwarp();  // every lane is done with this buffer before tile t+2 overwrites it
   }
 }
 
 template <int D, int R, bool GRAD>
-__device__ __forceinline__ void urow_reset(URow<D, R, GRAD> (&st)[R]) {
+__device__ __forceinline__ void urow_reset(URow<D, R, GRAD> (&st)[R], float inv_ncoef) {
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     st[k].mref = kNegBig;
-    st[k].nm = make_float2(-kNegBig, -kNegBig);
+    st[k].mu = make_float2(kNegBig * inv_ncoef, kNegBig * inv_ncoef);
     st[k].s = make_float2(0.f, 0.f);
 #pragma unroll
     for (int d = 0; d < (GRAD ? D : 1); ++d) st[k].g[d] = make_float2(0.f, 0.f);
@@ -234,17 +248,17 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
       const bool act = i < N;
       const int src = act ? i : 0;
       URow<D, 1, true> st[1];
-      urow_reset<D, 1, true>(st);
+      urow_reset<D, 1, true>(st, -1.0f / rc.coef);
 #pragma unroll
       for (int d = 0; d < D; ++d) st[0].nx[d] = -pts[(size_t)d * strideP + src];
-      stream_rows<D, 1, true>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane);
+      stream_rows<D, 1, true, false>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane);
       const float sS = st[0].s.x + st[0].s.y;
       const float S = rc.scale * (st[0].mref + lg2_approx(sS));
       float gS[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) gS[d] = (st[0].g[d].x + st[0].g[d].y) / sS;
-      urow_reset<D, 1, true>(st);
-      stream_rows<D, 1, true>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane);
+      urow_reset<D, 1, true>(st, -1.0f / rc.coef);
+      stream_rows<D, 1, true, false>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane);
       if (!act) continue;
       const float sC = st[0].s.x + st[0].s.y;
       const float C = rc.scale * (st[0].mref + lg2_approx(sC));
@@ -270,7 +284,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   const float* ch = (own ? hSc : hCc) + (cols_x ? 0 : p.nqMax);
   const int ncols = cols_x ? Nq : Mq;
   URow<D, R, false> st[R];
-  urow_reset<D, R, false>(st);
+  urow_reset<D, R, false>(st, -1.0f / rc.coef);
   int ridx[R];
 #pragma unroll
   for (int k = 0; k < R; ++k) {
@@ -280,7 +294,10 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
 #pragma unroll
     for (int d = 0; d < D; ++d) st[k].nx[d] = -pts[(size_t)d * strideP + src];
   }
-  stream_rows<D, R, false>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane);
+  // warm rounds (eps >= eps_0 / 256): reference exponent folded into the distance chain (one op less per pair)
+  const float eps0 = b.sched[(size_t)img * KDOT_MAX_ROUNDS].eps;
+  if (rc.eps * 256.0f >= eps0) stream_rows<D, R, false, true>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane);
+  else stream_rows<D, R, false, false>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane);
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     if (ridx[k] < 0) continue;
