@@ -58,7 +58,9 @@ enum {
  *
  * Replaces, per image i with N_i = cu_n[i+1]-cu_n[i] student and M_i teacher cells:
  *   - the in-place normalisation  xy[:,0] /= w ; xy[:,1] /= h        (losses/loss_libs.py:8-12)
- *     when normalize != 0 (requires D == 2); xs AND xt are overwritten with the normalised values;
+ *     when normalize != 0 (requires D == 2); xs AND xt are overwritten with the normalised values
+ *     (normalize == 2: normalise in registers WITHOUT the write-back -- small fused path only; used by the
+ *     host-buffer entry point when it lets the kernel read the caller's staging area directly);
  *   - the per-image split / transposes / SamplesLoss(...).sum() loop   (losses/loss_libs.py:22-50);
  *   - geomloss.SamplesLoss("sinkhorn", p, blur, scaling, reach) on the tensorized backend, i.e. the
  *     four cost matrices, max_diameter, the float64 epsilon schedule, the symmetrised log-domain

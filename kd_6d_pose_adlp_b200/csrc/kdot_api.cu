@@ -101,6 +101,8 @@ int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt
     return fail(KDOT_E_BADARG, "NULL required pointer");
   if (!stream_supports_dim(D)) return fail(KDOT_E_BADARG, "D must be one of 1, 2, 3, 4, 8, 16");
   if (normalize && D != 2) return fail(KDOT_E_BADARG, "normalize requires D == 2 (losses/loss_libs.py:7)");
+  if (normalize == 2 && !(small_path(max_n, max_m, B, D) && max_n + max_m <= 32))
+    return fail(KDOT_E_BADARG, "normalize == 2 (no write-back) is only available on the small fused path");
   if (p != 2.0f) return fail(KDOT_E_BADARG, "only p == 2 is implemented");
   if (!(blur > 0.f) || !(scaling > 0.f && scaling < 1.f)) return fail(KDOT_E_BADARG, "blur > 0 and 0 < scaling < 1 required");
   if (layout != KDOT_LAYOUT_CELL_MAJOR && layout != KDOT_LAYOUT_SLOT_MAJOR) return fail(KDOT_E_BADARG, "bad layout");
@@ -204,9 +206,9 @@ kdot_host_ctx* kdot_host_ctx_create(int device, int max_img, int max_cells_s, in
             cudaMalloc((void**)&c->dev_ws, c->cap_ws) == cudaSuccess;
   if (ok) {
     const char* env = getenv("KDOT_HOST_ZERO_COPY");
-    c->zero_copy = !(env && env[0] == '0') &&
-                   cudaHostGetDevicePointer((void**)&c->pin_in_dev, c->pin_in, 0) == cudaSuccess &&
-                   cudaHostGetDevicePointer((void**)&c->pin_out_dev, c->pin_out, 0) == cudaSuccess;
+    const bool mapped = cudaHostGetDevicePointer((void**)&c->pin_in_dev, c->pin_in, 0) == cudaSuccess &&
+                        cudaHostGetDevicePointer((void**)&c->pin_out_dev, c->pin_out, 0) == cudaSuccess;
+    c->zero_copy = !mapped ? 0 : (env ? atoi(env) : 1);
   }
   if (!ok) {
     g_err = std::string("kdot_host_ctx_create: ") + cudaGetErrorString(cudaGetLastError());
@@ -289,18 +291,25 @@ int kdot_sinkhorn_fwd_bwd_host(kdot_host_ctx* c, float* xs_h, const float* ws_h,
   const size_t out_bytes = q;
 
   const auto t1 = std::chrono::steady_clock::now();
-  // Inputs go through ONE copy-engine H2D transfer (the kernel re-reads them, so they must sit in HBM).  Small
-  // outputs are written by the kernel straight into the mapped pinned staging area (posted PCIe writes): that
-  // removes the D2H copy-engine launch (~8-10 us of fixed latency) from the critical path.  KDOT_HOST_ZERO_COPY=0
-  // restores the explicit D2H copy; larger outputs always use it.
-  const bool zc_out = c->zero_copy && out_bytes <= (1u << 20) && !(normalize && write_back_normalized);
+  // Host-buffer transport.  zero_copy = 0: explicit H2D + D2H copies.  1 (default): inputs by ONE copy-engine H2D
+  // transfer, small outputs written by the kernel straight into the mapped pinned staging area (posted PCIe writes;
+  // removes the D2H copy-engine launch, ~8-10 us of fixed latency).  2: small problems also READ their inputs from the
+  // mapped staging area (each element is read exactly once by the fused kernel), so the step is one kernel + one sync.
+  const bool small = small_path(max_n, max_m, B, D) && max_n + max_m <= 32;
+  const bool zc_out = c->zero_copy >= 1 && out_bytes <= (1u << 20) && !(normalize && write_back_normalized);
+  const bool zc_in = c->zero_copy >= 2 && small && zc_out && in_bytes <= (1u << 20);
+  char* in_base = zc_in ? c->pin_in_dev : c->dev_in;
   char* out_base = zc_out ? c->pin_out_dev : c->dev_out;
-  cudaError_t e = cudaMemcpyAsync(c->dev_in, c->pin_in, in_bytes, cudaMemcpyHostToDevice, c->stream);
-  if (e != cudaSuccess) return fail_cuda(e, "H2D");
-  int rc = kdot_sinkhorn_fwd_bwd((float*)(c->dev_in + o_xs), ws_h ? (const float*)(c->dev_in + o_ws) : nullptr,
-                                 (float*)(c->dev_in + o_xt), wt_h ? (const float*)(c->dev_in + o_wt) : nullptr,
-                                 (const int32_t*)(c->dev_in + o_cn), (const int32_t*)(c->dev_in + o_cm), nimg, B, D,
-                                 max_n, max_m, KDOT_LAYOUT_CELL_MAJOR, p, blur, reach, scaling, w, h, normalize,
+  cudaError_t e = cudaSuccess;
+  if (!zc_in) {
+    e = cudaMemcpyAsync(c->dev_in, c->pin_in, in_bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "H2D");
+  }
+  int rc = kdot_sinkhorn_fwd_bwd((float*)(in_base + o_xs), ws_h ? (const float*)(in_base + o_ws) : nullptr,
+                                 (float*)(in_base + o_xt), wt_h ? (const float*)(in_base + o_wt) : nullptr,
+                                 (const int32_t*)(in_base + o_cn), (const int32_t*)(in_base + o_cm), nimg, B, D,
+                                 max_n, max_m, KDOT_LAYOUT_CELL_MAJOR, p, blur, reach, scaling, w, h,
+                                 zc_in ? (normalize ? 2 : 0) : normalize,
                                  (float*)(out_base + q_loss), nullptr, (int32_t*)(out_base + q_valid),
                                  (float*)(out_base + q_gx), (float*)(out_base + q_gw),
                                  (int32_t*)(out_base + q_nits), c->dev_ws, c->cap_ws, c->stream);

@@ -175,8 +175,10 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
   c.col = c.isx ? lane : Nq + (lane - N);
   c.px = c.py = 0.f; c.wgt = 0.f; c.lw2 = 0.f;
 
-  // ---- image-wide bounding box over all B slots (every warp redundantly: no block barrier needed).  Division by a
-  //      positive constant is monotone, so the box of the normalised points is the normalised box of the raw ones. ----
+  // ---- every warp touches only ITS slot: load, normalise in place (the same thread reads and writes an element, so
+  //      there is no cross-warp hazard), log-weight.  The image-wide bounding box is assembled from the per-warp
+  //      boxes through shared memory, across the cluster through DSMEM. ----
+  __shared__ float s_box[16][4];
   float minx = 3.0e38f, miny = 3.0e38f, maxx = -3.0e38f, maxy = -3.0e38f;
   long long gidx = 0;
   float* base = nullptr;
@@ -186,33 +188,24 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
     const float* wsrc;
     if (c.isx) { base = prm.xs; cell = n0 + lane; s_cell = prm.s_cell_n; s_slot = prm.s_slot_n; wsrc = prm.ws; }
     else       { base = prm.xt; cell = m0 + lane - N; s_cell = prm.s_cell_m; s_slot = prm.s_slot_m; wsrc = prm.wt; }
-    for (int s0 = 0; s0 < B; s0 += 8) {  // all loads of a batch of 8 slots in flight together
-      float2 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        v[u] = *reinterpret_cast<const float2*>(base + 2 * (cell * s_cell + (long long)min(s0 + u, B - 1) * s_slot));
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        minx = fminf(minx, v[u].x); maxx = fmaxf(maxx, v[u].x);
-        miny = fminf(miny, v[u].y); maxy = fmaxf(maxy, v[u].y);
-        if (s0 + u == slot) { c.px = v[u].x; c.py = v[u].y; }
-      }
-    }
     gidx = cell * s_cell + (long long)slot * s_slot;
+    float2 v = *reinterpret_cast<const float2*>(base + 2 * gidx);
     c.wgt = wsrc ? wsrc[gidx] : __fdiv_rn(1.0f, (float)(c.isx ? N : M));
+    if (prm.normalize) {
+      v.x = __fdiv_rn(v.x, prm.w);
+      v.y = __fdiv_rn(v.y, prm.h);
+      if (prm.normalize == 1) *reinterpret_cast<float2*>(base + 2 * gidx) = v;  // 2: keep the caller's buffer raw
+    }
+    c.px = v.x; c.py = v.y;
+    minx = maxx = v.x;
+    miny = maxy = v.y;
     c.lw2 = (c.wgt > 0.f ? logf(c.wgt) : kLogZeroWeight) * kLog2e;
   }
   float* gx_out = prm.grad_xs + 2 * gidx;
   dbg_stamp(prm, img, 1);
-  if (prm.normalize) {
-    // every warp of every CTA of the image has read the RAW points of all slots before any slot is overwritten
-    if (split > 1) cluster.sync(); else __syncthreads();
-    if (c.act) {
-      c.px = __fdiv_rn(c.px, prm.w);
-      c.py = __fdiv_rn(c.py, prm.h);
-      *reinterpret_cast<float2*>(base + 2 * gidx) = make_float2(c.px, c.py);
-    }
-  }
+  minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
+  if (lane == 0) { s_box[warp][0] = minx; s_box[warp][1] = miny; s_box[warp][2] = maxx; s_box[warp][3] = maxy; }
+  if (split > 1) cluster.sync(); else __syncthreads();
 
   if (N == 0 || M == 0) {  // skipped image (loss_libs.py:25-28); uniform over the CTA
     if (c.act && c.isx) {
@@ -227,10 +220,12 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
     }
     return;
   }
-  minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
-  if (prm.normalize) {
-    minx = __fdiv_rn(minx, prm.w); maxx = __fdiv_rn(maxx, prm.w);
-    miny = __fdiv_rn(miny, prm.h); maxy = __fdiv_rn(maxy, prm.h);
+  for (int rk = 0; rk < split; ++rk) {
+    const float(*rb)[4] = split > 1 ? cluster.map_shared_rank(s_box, rk) : s_box;
+    for (int wi = 0; wi < wpc; ++wi) {
+      minx = fminf(minx, rb[wi][0]); miny = fminf(miny, rb[wi][1]);
+      maxx = fmaxf(maxx, rb[wi][2]); maxy = fmaxf(maxy, rb[wi][3]);
+    }
   }
   const float diam_f = bbox_diameter(minx, miny, maxx, maxy);
   dbg_stamp(prm, img, 2);
@@ -257,6 +252,7 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
       prm.valid[img] = status;
       if (prm.nits_per_img) prm.nits_per_img[img] = nits;
     }
+    if (split > 1) cluster.sync();  // no CTA of the cluster exits while a peer may still read its box
     return;
   }
 

@@ -24,7 +24,19 @@ namespace cg = cooperative_groups;
 
 namespace kdot {
 
-constexpr int kStreamThreads = 256;
+#ifndef KDOT_STREAM_THREADS
+#define KDOT_STREAM_THREADS 256
+#endif
+// tuning (tools/bench_variants.sh, dense_b32 on B200): D <= 2 runs best with 2 rows per lane at 64 registers and
+// 32 resident warps per SM (8.72 ms) -- more warps hide the SFU / FMA pipe contention better than more rows per lane
+// (4 rows, 124 registers, 16 warps: 9.44 ms)
+#ifndef KDOT_STREAM_MINBLOCKS
+#define KDOT_STREAM_MINBLOCKS 4
+#endif
+#ifndef KDOT_STREAM_R2
+#define KDOT_STREAM_R2 2
+#endif
+constexpr int kStreamThreads = KDOT_STREAM_THREADS;
 constexpr float kTauS = 24.f;
 
 struct StreamParams {
@@ -311,7 +323,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
 }
 
 template <int D, int R>
-__global__ void __launch_bounds__(kStreamThreads, 2) kdot_stream_kernel(StreamParams p) {
+__global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCKS : 2)) kdot_stream_kernel(StreamParams p) {
   cg::grid_group grid = cg::this_grid();
   const SinkhornParams& b = p.b;
   const int B = b.B;
@@ -515,7 +527,7 @@ struct StreamPlan {
   size_t off_pts, off_lw, off_pot, off_h, off_term, off_ctr, off_done, off_sched, off_rounds, total;
 };
 
-static int rows_per_lane(int D) { return D <= 2 ? 4 : (D <= 8 ? 2 : 1); }
+static int rows_per_lane(int D) { return D <= 2 ? KDOT_STREAM_R2 : (D <= 8 ? 2 : 1); }
 
 StreamPlan plan_stream(int nimg, int max_n, int max_m, int B, int D) {
   StreamPlan s;
@@ -582,8 +594,8 @@ cudaError_t launch_stream(const SinkhornParams& prm, int D, int max_n, int max_m
   sp.ctr = (unsigned int*)(base + pl.off_ctr);
   sp.done = (unsigned int*)(base + pl.off_done);
   switch (D) {
-    case 1: return launch_stream_t<1, 2>(sp, stream);
-    case 2: return launch_stream_t<2, 4>(sp, stream);
+    case 1: return launch_stream_t<1, KDOT_STREAM_R2>(sp, stream);
+    case 2: return launch_stream_t<2, KDOT_STREAM_R2>(sp, stream);
     case 3: return launch_stream_t<3, 2>(sp, stream);
     case 4: return launch_stream_t<4, 2>(sp, stream);
     case 8: return launch_stream_t<8, 2>(sp, stream);
