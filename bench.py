@@ -421,14 +421,14 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_dense and args.workload != "dense_b32":
         # secondary leg: the roofline-relevant dense configuration (BASELINE.json configs[2], variant 3b)
-        db = make_batch("dense_b32", 0, nimg=8)
+        db = make_batch("dense_b32", 0)
         dbench = DeviceBench(db, dev)
-        d_total, d_per, d_launch = dbench.timed(3, 1, lambda: None)
+        d_total, d_per, d_launch = dbench.timed(3, 3, lambda: None)
         d_ms = d_total / 3
         d_fl, d_ex, d_by = algorithmic_work(db, dbench.nits.cpu().numpy())
         line["dense"] = {
-            "workload": "dense_b32 (8-image sample)", "value": 8 / (d_ms * 1e-3), "unit": UNIT, "ms_per_step": d_ms,
-            "roofline": {"bound": "fp32", "kernel": "kdot_tiled_kernel", "achieved": d_fl / (d_ms * 1e-3) / 1e12,
+            "workload": "dense_b32", "value": len(db["pos_per_img"]) / (d_ms * 1e-3), "unit": UNIT, "ms_per_step": d_ms,
+            "roofline": {"bound": "fp32", "kernel": kernel_name(dbench.max_n, dbench.max_m, d_launch // 3), "achieved": d_fl / (d_ms * 1e-3) / 1e12,
                          "peak": fp32_peak, "unit": "TFLOP/s", "frac": d_fl / (d_ms * 1e-3) / 1e12 / fp32_peak,
                          "sfu_exp_per_s": d_ex / (d_ms * 1e-3), "traffic": None,
                          "hbm_gbs": d_by / (d_ms * 1e-3) / 1e9},

@@ -151,7 +151,7 @@ const char* kdot_last_error(void);
 int kdot_version(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 unsigned long long kdot_launch_count(void);
-/* profiling aid: when non-NULL, CTA 0-thread SM-clock stamps [nimg][8] (int64) are written by the small kernel */
+/* profiling aid: when non-NULL, CTA 0-thread [nimg][16] int64 SM-clock stamps (0-6), globaltimer (7) and exact-fallback count (8) are written by the small kernel */
 void kdot_debug_set_clock_buffer(void* dev_ptr);
 /* FP32 FMA-chain micro-benchmark: returns measured TFLOP/s of the device (roofline denominator) */
 double kdot_measure_fp32_peak_tflops(int device, int iters);

@@ -59,11 +59,11 @@ struct SinkhornParams {
   int32_t* sched_rounds; // [nimg] number of rounds (nits + 2) or <0 status
   float* slot_loss;      // [nimg][B]
   unsigned int* done_ctr; // [nimg]
-  long long* dbg_clk;     // optional [nimg][8] SM-clock stamps (kdot_debug_set_clock_buffer), NULL in production
+  long long* dbg_clk;     // optional [nimg][16] SM-clock stamps / counters (kdot_debug_set_clock_buffer), NULL in production
 };
 
 __device__ __forceinline__ void dbg_stamp(const SinkhornParams& p, int img, int k) {
-  if (p.dbg_clk && threadIdx.x == 0) p.dbg_clk[(size_t)img * 8 + k] = clock64();
+  if (p.dbg_clk && threadIdx.x == 0) p.dbg_clk[(size_t)img * 16 + k] = clock64();
 }
 
 __device__ __forceinline__ float warp_min(float v) {

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
   if (prm.dbg_clk && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    prm.dbg_clk[(size_t)img * 8 + 7] = (long long)t;
+    prm.dbg_clk[(size_t)img * 16 + 7] = (long long)t;
   }
   FastCtx c;
   c.cx = wbase_s; c.cy = wbase_s + kFastMaxCols; c.hb = wbase_s + 2 * kFastMaxCols;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
   if (threadIdx.x == 0 && part == 0) {
     double tot = 0.0;
     for (int s = 0; s < B; ++s) tot += s_slot_loss[s];  // fixed order: deterministic
-    if (prm.dbg_clk) prm.dbg_clk[(size_t)img * 8 + 6] = clock64();
+    if (prm.dbg_clk) prm.dbg_clk[(size_t)img * 16 + 6] = clock64();
     prm.loss_per_img[img] = (float)tot;
     prm.valid[img] = KDOT_IMG_OK;
     if (prm.nits_per_img) prm.nits_per_img[img] = nits;

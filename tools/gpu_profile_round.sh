@@ -13,8 +13,12 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:kdot_small_fast -s 3 -c 1 -o gpurun_out/${R}_prof_small_fast \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-dense > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:kdot_tiled -c 1 -o gpurun_out/${R}_prof_tiled \
+ncu --set full --clock-control none --import-source on -k regex:kdot_stream -c 1 -o gpurun_out/${R}_prof_stream \
     python bench.py --workload dense_b32 --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+KDOT_FORCE_PATH=tiled ncu --set full --clock-control none --import-source on -k regex:kdot_tiled -c 1 -o gpurun_out/${R}_prof_tiled \
+    python bench.py --workload dense_b32 --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/${R}_launches_dense_b32.csv \
+    python bench.py --workload dense_b32 --steps 3 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:kdot_select -c 1 -o gpurun_out/${R}_prof_select \
     python -m pytest tests/test_postprocess_gpu.py -m gpu -q -k bit_exact > /dev/null 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/${R}_nvidia_smi.csv

@@ -51,7 +51,7 @@ us, ni = run(64, 0.5, False, n_range=(16, 16)); print("nimg=64 N=M=16 warm:", us
 
 # ---- in-kernel clock stamps (kdot_debug_set_clock_buffer) ----
 nimg = 64
-clk = torch.zeros(nimg, 8, dtype=torch.int64, device=dev)
+clk = torch.zeros(nimg, 16, dtype=torch.int64, device=dev)
 L.kdot_debug_set_clock_buffer(clk.data_ptr())
 us, ni = run(nimg, 0.5, False, reps=10)
 L.kdot_debug_set_clock_buffer(None)
