@@ -321,6 +321,22 @@ def kernel_name(max_n, max_m, launches_per_step):
     return "kdot_tiled_kernel" if launches_per_step == 2 else "kdot_stream_kernel"
 
 
+def ncu_traffic_bytes(kernel):
+    """DRAM bytes (read + write) of one launch of `kernel` from the committed `ncu --set full` summary of the same
+    workload (profiles/r01_prof_*_ncu_summary.txt), or None when no capture is on file."""
+    tag = {"kdot_small_fast_kernel": "small_fast", "kdot_stream_kernel": "stream", "kdot_tiled_kernel": "tiled"}.get(kernel)
+    path = os.path.join(ROOT, "profiles", f"r01_prof_{tag}_ncu_summary.txt")
+    if tag is None or not os.path.exists(path):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    for line in open(path):
+        f = line.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            total += float(f[1].replace(",", "")) * unit.get(f[2], 1.0)
+    return total or None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -395,12 +411,15 @@ def main():
         "achieved": flops / (ms_per_step * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": flops / (ms_per_step * 1e-3) / 1e12 / fp32_peak if fp32_peak > 0 else None,
         "peak_source": "FP32 FMA chain measured live on this GPU (kdot_measure_fp32_peak_tflops)",
-        "traffic": None,
+        "traffic": None,  # filled below from the committed ncu capture of this kernel / workload
         "sfu_exp_per_s": exps / (ms_per_step * 1e-3),
         "hbm": {"achieved": byts / (ms_per_step * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                 "frac": byts / (ms_per_step * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6552.0), "peak_source": peak_src},
         "algorithmic_flops_per_step": flops, "algorithmic_bytes_per_step": byts, "median_ms_per_step": med_ms,
     }
+
+    roofline["traffic"] = ncu_traffic_bytes(roofline["kernel"])
+    roofline["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/)"
 
     # end to end through the host-buffer C-ABI call
     e2e_dt, h2d, d2h, mean_loss = host_e2e(batch, local_rank, args.steps, args.warmup, barrier)
@@ -430,7 +449,9 @@ def main():
             "workload": "dense_b32", "value": len(db["pos_per_img"]) / (d_ms * 1e-3), "unit": UNIT, "ms_per_step": d_ms,
             "roofline": {"bound": "fp32", "kernel": kernel_name(dbench.max_n, dbench.max_m, d_launch // 3), "achieved": d_fl / (d_ms * 1e-3) / 1e12,
                          "peak": fp32_peak, "unit": "TFLOP/s", "frac": d_fl / (d_ms * 1e-3) / 1e12 / fp32_peak,
-                         "sfu_exp_per_s": d_ex / (d_ms * 1e-3), "traffic": None,
+                         "sfu_exp_per_s": d_ex / (d_ms * 1e-3),
+                         "traffic": ncu_traffic_bytes(kernel_name(dbench.max_n, dbench.max_m, d_launch // 3)),
+                         "algorithmic_bytes_per_step": d_by,
                          "hbm_gbs": d_by / (d_ms * 1e-3) / 1e9},
         }
         del dbench
