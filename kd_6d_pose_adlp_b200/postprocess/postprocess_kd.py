@@ -65,7 +65,40 @@ def select_cells(box_cls, box_regression, anchor_sizes, anchor_strides, inferenc
     return out
 
 
-class PostProcessorKD(nn.Module):
+def _pnp_per_label(sel_np, i, targets_i, ncls, class_filter=None):
+    """Host part of ``pose_infer_ml`` (``postprocess_kd.py:158-203`` / ``postprocess.py:150-202``) for image ``i``:
+    for every candidate label (ascending), un-crop the selected key-points and run RANSAC-EPnP.
+    Yields ``(class_id, scores (n,), xy2d (n,8,2) float32 tensor, R, T)`` for every label whose PnP succeeded."""
+    import cv2
+
+    count, valid, score, kpts = sel_np["count"], sel_np["valid"], sel_np["score"], sel_np["kpts"]
+    K_np = targets_i.K.detach().cpu().numpy()
+    for c in range(ncls):
+        if valid[i, c].sum() == 0 or count[i, c] == 0:
+            continue
+        if class_filter is not None and c not in class_filter:
+            continue
+        n = int(count[i, c])
+        xy2d = torch.from_numpy(kpts[i, c, :n].copy()).view(n, 2, 8).transpose(1, 2).contiguous()  # (n,8,2)
+        if targets_i.bbox_trans is not None:
+            bt = targets_i.bbox_trans.detach().cpu().to(torch.float32).view(1, 2, 3).repeat(n, 1, 1)
+            lin, off = bt[:, :, :2], bt[:, :, 2].unsqueeze(-1)
+            xy2d = torch.bmm(torch.inverse(lin), xy2d.transpose(1, 2).contiguous() - off).transpose(1, 2).contiguous()
+        xy3d_np = targets_i.keypoints_3d[c].detach().cpu().repeat(n, 1, 1).view(-1, 3).numpy()
+        ok, rot, trans, _inl = cv2.solvePnPRansac(xy3d_np, xy2d.view(-1, 2).numpy(), K_np, None,
+                                                  flags=cv2.SOLVEPNP_EPNP, reprojectionError=5.0)
+        if not ok:
+            continue
+        R = cv2.Rodrigues(rot)[0]
+        T = trans.reshape(-1, 1)
+        if np.isnan(R.sum()) or np.isnan(T.sum()):
+            continue
+        yield c, score[i, c, :n].copy(), xy2d, R, T
+
+
+class _SelectingPostProcessor(nn.Module):
+    """Shared device part: ONE ``kdot_select_cells`` launch + ONE device->host copy of the selected cells."""
+
     def __init__(self, inference_th, box_coder, positive_num, positive_lambda, sym_types, symmetry_fn=None):
         super().__init__()
         self.inference_th = inference_th
@@ -73,62 +106,48 @@ class PostProcessorKD(nn.Module):
         self.positive_lambda = positive_lambda
         self.box_coder = box_coder
         self.sym_types = sym_types
-        self.symmetry_fn = symmetry_fn  # libs.utils.pose_symmetry_handling of the host repo (R only; unused by KD)
+        self.symmetry_fn = symmetry_fn  # libs.utils.pose_symmetry_handling of the host repo (rotation only)
         self.last_selection = None
 
-    def forward(self, box_cls, box_regression, targets, anchors=None):
-        import cv2
-
+    def _select(self, box_cls, box_regression):
         sel = select_cells(box_cls, box_regression, self.box_coder.anchor_sizes, self.box_coder.anchor_strides,
                            self.inference_th, self.positive_num, self.positive_lambda)
-        dev = box_cls[0].device
         nimg, ncls, cap = sel["nimg"], sel["ncls"], sel["cap"]
-        # one device->host copy for everything the host part needs
-        count = sel["sel_count"].cpu().numpy().reshape(nimg, ncls)
-        valid = sel["valid_cnt"].cpu().numpy().reshape(nimg, ncls, -1)
-        score = sel["sel_score"].cpu().numpy().reshape(nimg, ncls, cap)
-        kpts = sel["sel_kpts"].cpu().numpy().reshape(nimg, ncls, cap, 16)
-        self.last_selection = dict(count=count, valid=valid, score=score, kpts=kpts,
-                                   level=sel["sel_level"].cpu().numpy().reshape(nimg, ncls, cap),
-                                   loc=sel["sel_loc"].cpu().numpy().reshape(nimg, ncls, cap),
-                                   nk=sel["nk"].cpu().numpy().reshape(nimg, ncls, -1),
-                                   best=sel["best"].cpu().numpy().reshape(nimg, ncls, 2))
+        self.last_selection = dict(
+            count=sel["sel_count"].cpu().numpy().reshape(nimg, ncls),
+            valid=sel["valid_cnt"].cpu().numpy().reshape(nimg, ncls, -1),
+            score=sel["sel_score"].cpu().numpy().reshape(nimg, ncls, cap),
+            kpts=sel["sel_kpts"].cpu().numpy().reshape(nimg, ncls, cap, 16),
+            level=sel["sel_level"].cpu().numpy().reshape(nimg, ncls, cap),
+            loc=sel["sel_loc"].cpu().numpy().reshape(nimg, ncls, cap),
+            nk=sel["nk"].cpu().numpy().reshape(nimg, ncls, -1),
+            best=sel["best"].cpu().numpy().reshape(nimg, ncls, 2))
+        return nimg, ncls
+
+    def _symmetry(self, c, R):
+        if self.sym_types is not None and len(self.sym_types) > 0 and ("cls_" + str(c)) in self.sym_types:
+            if self.symmetry_fn is None:
+                from libs.utils import pose_symmetry_handling  # host repository
+
+                self.symmetry_fn = pose_symmetry_handling
+            R = self.symmetry_fn(R, self.sym_types["cls_" + str(c)])
+        return R
+
+
+class PostProcessorKD(_SelectingPostProcessor):
+    """Teacher knowledge extraction (``postprocess/postprocess_kd.py:12``): first label whose PnP succeeds."""
+
+    def forward(self, box_cls, box_regression, targets, anchors=None):
+        nimg, ncls = self._select(box_cls, box_regression)
+        dev = box_cls[0].device
         results = [[], [], [], []]
         for i in range(nimg):
-            picked = None
-            tgt = targets[i]
-            K_np = tgt.K.detach().cpu().numpy()
-            for c in range(ncls):  # candidate labels in ascending order (torch.unique), first success wins
-                if valid[i, c].sum() == 0 or count[i, c] == 0:
-                    continue
-                n = int(count[i, c])
-                sc = torch.from_numpy(np.broadcast_to(score[i, c, :n, None], (n, 8)).copy())
-                xy2d = torch.from_numpy(kpts[i, c, :n].copy()).view(n, 2, 8).transpose(1, 2).contiguous()  # (n,8,2)
-                if tgt.bbox_trans is not None:
-                    bt = tgt.bbox_trans.detach().cpu().to(torch.float32).view(1, 2, 3).repeat(n, 1, 1)
-                    lin, off = bt[:, :, :2], bt[:, :, 2].unsqueeze(-1)
-                    xy2d = torch.bmm(torch.inverse(lin), xy2d.transpose(1, 2).contiguous() - off).transpose(1, 2).contiguous()
-                xy3d_np = tgt.keypoints_3d[c].detach().cpu().repeat(n, 1, 1).view(-1, 3).numpy()
-                ok, rot, trans, _inl = cv2.solvePnPRansac(xy3d_np, xy2d.view(-1, 2).numpy(), K_np, None,
-                                                          flags=cv2.SOLVEPNP_EPNP, reprojectionError=5.0)
-                if not ok:
-                    continue
-                R = cv2.Rodrigues(rot)[0]
-                T = trans.reshape(-1, 1)
-                if np.isnan(R.sum()) or np.isnan(T.sum()):
-                    continue
-                picked = (sc, c, R, T, xy2d)
-                break
+            picked = next(_pnp_per_label(self.last_selection, i, targets[i], ncls), None)
             if picked is not None:
-                sc, c, R, T, xy2d = picked
-                if self.sym_types is not None and len(self.sym_types) > 0 and ("cls_" + str(c)) in self.sym_types:
-                    if self.symmetry_fn is None:
-                        from libs.utils import pose_symmetry_handling  # host repository
-
-                        self.symmetry_fn = pose_symmetry_handling
-                    R = self.symmetry_fn(R, self.sym_types["cls_" + str(c)])
-                results[0].append(sc.to(dev))
-                results[1].append(R)
+                c, sc, xy2d, R, T = picked
+                n = len(sc)
+                results[0].append(torch.from_numpy(np.broadcast_to(sc[:, None], (n, 8)).copy()).to(dev))
+                results[1].append(self._symmetry(c, R))
                 results[2].append(T)
                 results[3].append(xy2d.to(dev))
             else:
@@ -136,6 +155,23 @@ class PostProcessorKD(nn.Module):
                 results[1].append(torch.zeros([0, 3, 3]))
                 results[2].append(torch.zeros([0, 3, 1]))
                 results[3].append(torch.zeros([0, 8, 2], device=dev))
+        return results
+
+
+class PostProcessor(_SelectingPostProcessor):
+    """Student evaluation post-processor (``postprocess/postprocess.py:12``): the same
+    selection, restricted to the classes present in the target (``postprocess.py:111-113``), every label kept:
+    per image a list of ``[max score, class id, R, T, xy2d (n,8,2)]``."""
+
+    def forward(self, box_cls, box_regression, targets, anchors=None):
+        nimg, ncls = self._select(box_cls, box_regression)
+        results = []
+        for i in range(nimg):
+            present = set(int(v) for v in targets[i].class_ids.detach().cpu().reshape(-1).tolist())
+            per_img = []
+            for c, sc, xy2d, R, T in _pnp_per_label(self.last_selection, i, targets[i], ncls, class_filter=present):
+                per_img.append([float(sc.max()), int(c), self._symmetry(c, R), T, xy2d])
+            results.append(per_img)
         return results
 
 

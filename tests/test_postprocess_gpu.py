@@ -84,3 +84,33 @@ def test_empty_image_gives_empty_tensors():
     pp = PostProcessorKD(0.1, TargetCoder("POINT", scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES), 10, 1.0, {})
     pt = teacher_knowledge(pp, cls, reg, tg)
     assert pt["post_pos_per_img"] == [0, 0] and pt["post_kp_2d"].shape == (0, 8, 2) and pt["post_kp_cls"].shape == (0, 8)
+
+
+def test_student_eval_postprocessor_same_selection():
+    """PostProcessor (student evaluation, postprocess/postprocess.py) shares the selection kernel: same cells, all
+    labels of the target kept, score = max over the selected cells."""
+    from kd_6d_pose_adlp_b200.postprocess.postprocess_kd import PostProcessor
+    from kd_6d_pose_adlp_b200.target_coder import TargetCoder
+
+    z, pp_kd, res_kd, t_cls = _setup()
+    dev = torch.device("cuda:0")
+    nimg, seed = int(z["nimg"]), int(z["seed"])
+    t_cls, t_reg = scenario.make_head_outputs(nimg, T_HW, seed + 100, teacher=True, target_seed=seed)
+    targets = []
+    for i in range(nimg):
+        t = doubles.Target(torch.tensor(z["K"]), torch.tensor(z["keypoints_3d"]), torch.tensor(z["bbox_trans"][i]))
+        t.class_ids = torch.tensor([0])
+        targets.append(t)
+    pp = PostProcessor(0.1, TargetCoder("POINT", scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES), 10, 1.0, {})
+    out = pp([torch.from_numpy(a).to(dev) for a in t_cls], [torch.from_numpy(a).to(dev) for a in t_reg], targets, None)
+    assert len(out) == nimg
+    for i in range(nimg):
+        assert len(out[i]) == 1 and out[i][0][1] == 0
+        score, cls_id, R, T, xy2d = out[i][0]
+        assert abs(score - float(res_kd[0][i].max())) < 1e-6
+        assert np.allclose(xy2d.numpy(), res_kd[3][i].cpu().numpy(), atol=1e-4)
+        assert R.shape == (3, 3) and T.shape == (3, 1)
+    # a target that does not contain class 0 yields nothing for that image
+    targets[0].class_ids = torch.tensor([3])
+    out = pp([torch.from_numpy(a).to(dev) for a in t_cls], [torch.from_numpy(a).to(dev) for a in t_reg], targets, None)
+    assert out[0] == [] and len(out[1]) == 1
