@@ -92,6 +92,19 @@ int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt
                           float* grad_xs, float* grad_ws, int32_t* nits_per_img,
                           void* workspace, size_t workspace_bytes, void* cuda_stream);
 
+/*
+ * Kernel-MMD sample losses, fused forward + backward: SamplesLoss("gaussian" | "laplacian" | "energy", blur)
+ * (--gtype of arguments/argument_kd.py:41 -> losses/kd_loss.py:26-30; geomloss kernel_tensorized):
+ *   loss = 1/2 <a, K_xx a> + 1/2 <b, K_yy b> - <a, K_xy b>,  kind 0: exp(-|x-y|^2 / 2 blur^2), 1: exp(-|x-y| / blur),
+ *   2: -|x-y|.  Same layouts, normalisation, skip rule and outputs as kdot_sinkhorn_fwd_bwd (no workspace, no rounds).
+ */
+int kdot_kernel_mmd_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt,
+                            const int32_t* cu_n, const int32_t* cu_m, int nimg, int B, int D,
+                            int max_n, int max_m, int layout, int kind, float blur,
+                            float w, float h, int normalize,
+                            float* loss_per_img, float* loss_per_slot, int32_t* valid,
+                            float* grad_xs, float* grad_ws, void* cuda_stream);
+
 /* Bytes of device scratch kdot_sinkhorn_fwd_bwd needs for these bounds (0 is a valid answer). */
 size_t kdot_workspace_bytes(int nimg, int max_n, int max_m, int B, int D);
 

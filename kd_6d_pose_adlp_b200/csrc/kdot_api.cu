@@ -18,6 +18,7 @@ size_t tiled_smem_bytes(int max_n, int max_m);
 cudaError_t launch_stream(const SinkhornParams& prm, int D, int max_n, int max_m, void* workspace, cudaStream_t stream);
 size_t stream_workspace_bytes(int nimg, int max_n, int max_m, int B, int D);
 bool stream_supports_dim(int D);
+cudaError_t launch_mmd(const SinkhornParams& prm, int D, int kind, float blur, cudaStream_t stream);
 
 static thread_local std::string g_err;
 static std::atomic<unsigned long long> g_launches{0};
@@ -160,6 +161,40 @@ int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt
   if (too_large) return fail(KDOT_E_TOOLARGE, "cloud does not fit the tiled kernel's shared-memory plan");
   if (e != cudaSuccess) return fail_cuda(e, "kdot_tiled_kernel");
   count_launches(2);
+  return KDOT_OK;
+}
+
+int kdot_kernel_mmd_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt, const int32_t* cu_n,
+                            const int32_t* cu_m, int nimg, int B, int D, int max_n, int max_m, int layout, int kind,
+                            float blur, float w, float h, int normalize, float* loss_per_img, float* loss_per_slot,
+                            int32_t* valid, float* grad_xs, float* grad_ws, void* cuda_stream) {
+  if (nimg == 0) return KDOT_OK;
+  if (nimg < 0 || B <= 0 || max_n < 0 || max_m < 0) return fail(KDOT_E_BADARG, "negative size");
+  if (!xs || !xt || !cu_n || !cu_m || !loss_per_img || !valid || !grad_xs) return fail(KDOT_E_BADARG, "NULL required pointer");
+  if (D < 1 || D > 16) return fail(KDOT_E_BADARG, "D must be in 1..16");
+  if (kind < 0 || kind > 2) return fail(KDOT_E_BADARG, "kind must be 0 (gaussian), 1 (laplacian) or 2 (energy)");
+  if (kind != 2 && !(blur > 0.f)) return fail(KDOT_E_BADARG, "blur > 0 required");
+  if (layout != KDOT_LAYOUT_CELL_MAJOR && layout != KDOT_LAYOUT_SLOT_MAJOR) return fail(KDOT_E_BADARG, "bad layout");
+  if (layout == KDOT_LAYOUT_SLOT_MAJOR && nimg != 1) return fail(KDOT_E_BADARG, "slot-major layout requires nimg == 1");
+  if (normalize && (D != 2 || !(w > 0.f && h > 0.f))) return fail(KDOT_E_BADARG, "normalize needs D == 2 and w, h > 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KDOT_E_NODEVICE, "no CUDA device: libkdot has no CPU fallback");
+  SinkhornParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.xs = xs; prm.ws = ws; prm.xt = xt; prm.wt = wt;
+  prm.cu_n = cu_n; prm.cu_m = cu_m;
+  prm.nimg = nimg; prm.B = B;
+  if (layout == KDOT_LAYOUT_CELL_MAJOR) {
+    prm.s_cell_n = B; prm.s_slot_n = 1; prm.s_cell_m = B; prm.s_slot_m = 1;
+  } else {
+    prm.s_cell_n = 1; prm.s_slot_n = max_n; prm.s_cell_m = 1; prm.s_slot_m = max_m;
+  }
+  prm.w = w; prm.h = h; prm.normalize = normalize;
+  prm.loss_per_img = loss_per_img; prm.loss_per_slot = loss_per_slot; prm.valid = valid;
+  prm.grad_xs = grad_xs; prm.grad_ws = grad_ws;
+  cudaError_t e = launch_mmd(prm, D, kind, blur, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return fail_cuda(e, "kdot_mmd_kernel");
+  count_launches(1);
   return KDOT_OK;
 }
 

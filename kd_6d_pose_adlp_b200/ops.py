@@ -25,6 +25,7 @@ class OTConfig:
     blur: float = 0.001
     scaling: float = 0.5
     reach: Optional[float] = 0.5  # None -> balanced OT
+    loss: str = "sinkhorn"        # or "gaussian" / "laplacian" / "energy" (kernel MMD, --gtype)
 
 
 _workspaces = {}
@@ -99,6 +100,17 @@ def ot_loss_batched(xs, ws, xt, wt, pos_per_img, pos_per_img_t, cfg: OTConfig = 
     nits = torch.empty(nimg, dtype=torch.int32, device=dev)
     grad_xs = torch.empty_like(xs)
     grad_ws = torch.empty(xs.shape[:2], dtype=torch.float32, device=dev)
+    if cfg.loss != "sinkhorn":
+        kind = {"gaussian": 0, "laplacian": 1, "energy": 2}[cfg.loss]
+        with torch.cuda.device(dev):
+            rc = L.kdot_kernel_mmd_fwd_bwd(
+                _ptr(xs), _ptr(ws), _ptr(xt), _ptr(wt), _ptr(cu_n), _ptr(cu_m), nimg, B, D, max_n, max_m, layout, kind,
+                float(cfg.blur), float(w), float(h), 1 if normalize else 0,
+                _ptr(loss), _ptr(slots), _ptr(valid), _ptr(grad_xs), _ptr(grad_ws),
+                torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "kdot_kernel_mmd_fwd_bwd")
+        nits.zero_()
+        return dict(loss_per_img=loss, loss_per_slot=slots, valid=valid, grad_xs=grad_xs, grad_ws=grad_ws, nits=nits)
     ws_bytes = int(L.kdot_workspace_bytes(nimg, max_n, max_m, B, D))
     wsp = _workspace(dev, ws_bytes)
     with torch.cuda.device(dev):

@@ -37,8 +37,8 @@ class _SamplesLossFunction(torch.autograd.Function):
 class SamplesLoss(torch.nn.Module):
     """Debiased (un)balanced Sinkhorn divergence ``S_eps,rho(alpha, beta)`` between weighted point clouds.
 
-    Only what the reference's flags can reach on its hot path is implemented natively: ``loss="sinkhorn"``,
-    ``p=2``, ``debias=True``, ``potentials=False``, tensorized semantics.  Anything else raises
+    What the reference's flags can reach is implemented natively: ``loss="sinkhorn"`` (``p=2``, ``debias=True``,
+    ``potentials=False``, tensorized semantics) and the kernel-MMD losses ``"gaussian"``, ``"laplacian"``, ``"energy"``.  Anything else raises
     ``NotImplementedError`` -- there is no fallback to a slower implementation.
     """
 
@@ -46,9 +46,9 @@ class SamplesLoss(torch.nn.Module):
                  cost=None, kernel=None, cluster_scale=None, debias=True, potentials=False, verbose=False,
                  backend="auto"):
         super().__init__()
-        if loss != "sinkhorn":
-            raise NotImplementedError(f"SamplesLoss(loss={loss!r}): only 'sinkhorn' has a CUDA kernel")
-        if float(p) != 2.0:
+        if loss not in ("sinkhorn", "gaussian", "laplacian", "energy"):
+            raise NotImplementedError(f"SamplesLoss(loss={loss!r}): no CUDA kernel (sinkhorn, gaussian, laplacian, energy)")
+        if loss == "sinkhorn" and float(p) != 2.0:
             raise NotImplementedError("SamplesLoss: only p=2 has a CUDA kernel")
         if diameter is not None or cost is not None or kernel is not None or not debias or potentials:
             raise NotImplementedError("SamplesLoss: diameter/cost/kernel/debias=False/potentials are not supported")
@@ -62,7 +62,7 @@ class SamplesLoss(torch.nn.Module):
     @property
     def config(self) -> OTConfig:
         return OTConfig(p=self.p, blur=self.blur, scaling=self.scaling,
-                        reach=None if self.reach is None else float(self.reach))
+                        reach=None if self.reach is None else float(self.reach), loss=self.loss)
 
     def forward(self, *args):
         if len(args) == 4:

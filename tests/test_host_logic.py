@@ -13,13 +13,14 @@ from kd_6d_pose_adlp_b200.target_coder import TargetCoder, grid_anchors
 
 def test_samples_loss_rejects_what_has_no_kernel():
     with pytest.raises(NotImplementedError):
-        SamplesLoss("gaussian")
+        SamplesLoss("l1")                       # --gtype l1 / l2 are not geomloss losses either
+    assert SamplesLoss("gaussian", blur=0.05).config.loss == "gaussian"
     with pytest.raises(NotImplementedError):
         SamplesLoss("sinkhorn", p=1)
     with pytest.raises(NotImplementedError):
         SamplesLoss("sinkhorn", p=2, debias=False)
     L = SamplesLoss("sinkhorn", p=2.0, blur=0.001, scaling=0.5, reach=0.5)
-    assert L.config == OTConfig(2.0, 0.001, 0.5, 0.5)
+    assert L.config == OTConfig(2.0, 0.001, 0.5, 0.5, "sinkhorn")
     with pytest.raises(ValueError):
         L(torch.zeros(8, 3, 2), torch.zeros(8, 3))            # dims differ
     with pytest.raises(ValueError):
