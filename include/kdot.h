@@ -69,7 +69,7 @@ enum {
  *   - autograd's backward of all of the above w.r.t. the student points and masses.
  *
  * ws / wt may be NULL: uniform 1/N_i, 1/M_i masses (losses/loss_libs.py:49, --weightedOT false).
- * reach < 0 selects balanced OT (geomloss reach=None).  Only p == 2 is implemented.
+ * reach < 0 selects balanced OT (geomloss reach=None).  p == 2 (cost |x-y|^2/2) or p == 1 (cost |x-y|, D == 2 only).
  *
  * Outputs
  *   loss_per_img [nimg]    sum over the B slots of the Sinkhorn divergence (the `.sum()` of
@@ -107,6 +107,8 @@ int kdot_kernel_mmd_fwd_bwd(float* xs, const float* ws, float* xt, const float* 
 
 /* Bytes of device scratch kdot_sinkhorn_fwd_bwd needs for these bounds (0 is a valid answer). */
 size_t kdot_workspace_bytes(int nimg, int max_n, int max_m, int B, int D);
+/* same, for a given p (p == 1 always runs on the streaming kernel and needs its scratch even for small clouds) */
+size_t kdot_workspace_bytes_ex(int nimg, int max_n, int max_m, int B, int D, float p);
 
 /*
  * Host-buffer convenience around kdot_sinkhorn_fwd_bwd for callers that hold NumPy / C arrays

@@ -17,7 +17,7 @@ KDOT_MAX_ROUNDS = 1024
 
 # every symbol include/kdot.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = (
-    "kdot_sinkhorn_fwd_bwd", "kdot_kernel_mmd_fwd_bwd", "kdot_workspace_bytes", "kdot_host_ctx_create", "kdot_host_ctx_destroy",
+    "kdot_sinkhorn_fwd_bwd", "kdot_kernel_mmd_fwd_bwd", "kdot_workspace_bytes", "kdot_workspace_bytes_ex", "kdot_host_ctx_create", "kdot_host_ctx_destroy",
     "kdot_sinkhorn_fwd_bwd_host", "kdot_host_ctx_last_traffic", "kdot_host_ctx_last_timing", "kdot_select_cells", "kdot_last_error",
     "kdot_version", "kdot_launch_count", "kdot_measure_fp32_peak_tflops", "kdot_debug_set_clock_buffer",
 )
@@ -47,6 +47,8 @@ def lib():
     L.kdot_launch_count.restype = C.c_ulonglong
     L.kdot_workspace_bytes.restype = sz
     L.kdot_workspace_bytes.argtypes = [i32] * 5
+    L.kdot_workspace_bytes_ex.restype = sz
+    L.kdot_workspace_bytes_ex.argtypes = [i32] * 5 + [f32]
     L.kdot_sinkhorn_fwd_bwd.restype = i32
     L.kdot_sinkhorn_fwd_bwd.argtypes = (
         [vp] * 6 + [i32] * 6 + [f32] * 6 + [i32] + [vp] * 6 + [vp, sz, vp]

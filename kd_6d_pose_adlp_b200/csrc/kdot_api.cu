@@ -85,6 +85,12 @@ int kdot_version(void) { return KDOT_VERSION; }
 void kdot_debug_set_clock_buffer(void* dev_ptr) { g_dbg_clk = (long long*)dev_ptr; }
 unsigned long long kdot_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+size_t kdot_workspace_bytes_ex(int nimg, int max_n, int max_m, int B, int D, float p) {
+  if (nimg <= 0) return 0;
+  if (p == 1.0f) return stream_supports_dim(D) ? stream_workspace_bytes(nimg, max_n, max_m, B, D) : 0;
+  return kdot_workspace_bytes(nimg, max_n, max_m, B, D);
+}
+
 size_t kdot_workspace_bytes(int nimg, int max_n, int max_m, int B, int D) {
   if (nimg <= 0 || small_path(max_n, max_m, B, D)) return 0;
   if (large_path(max_n, max_m, D) == 0) return plan_workspace(nimg, B).total;
@@ -102,9 +108,10 @@ int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt
     return fail(KDOT_E_BADARG, "NULL required pointer");
   if (!stream_supports_dim(D)) return fail(KDOT_E_BADARG, "D must be one of 1, 2, 3, 4, 8, 16");
   if (normalize && D != 2) return fail(KDOT_E_BADARG, "normalize requires D == 2 (losses/loss_libs.py:7)");
-  if (normalize == 2 && !(small_path(max_n, max_m, B, D) && max_n + max_m <= 32))
+  if (normalize == 2 && !(p == 2.0f && small_path(max_n, max_m, B, D) && max_n + max_m <= 32))
     return fail(KDOT_E_BADARG, "normalize == 2 (no write-back) is only available on the small fused path");
-  if (p != 2.0f) return fail(KDOT_E_BADARG, "only p == 2 is implemented");
+  if (p != 2.0f && p != 1.0f) return fail(KDOT_E_BADARG, "p must be 1 or 2");
+  if (p == 1.0f && D != 2) return fail(KDOT_E_BADARG, "p == 1 is implemented for D == 2 only");
   if (!(blur > 0.f) || !(scaling > 0.f && scaling < 1.f)) return fail(KDOT_E_BADARG, "blur > 0 and 0 < scaling < 1 required");
   if (layout != KDOT_LAYOUT_CELL_MAJOR && layout != KDOT_LAYOUT_SLOT_MAJOR) return fail(KDOT_E_BADARG, "bad layout");
   if (layout == KDOT_LAYOUT_SLOT_MAJOR && nimg != 1) return fail(KDOT_E_BADARG, "slot-major layout requires nimg == 1");
@@ -136,15 +143,16 @@ int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt
   prm.dbg_clk = g_dbg_clk;
   cudaStream_t stream = (cudaStream_t)cuda_stream;
 
-  if (small_path(max_n, max_m, B, D)) {
+  const bool p1 = p == 1.0f;  // cost |x - y|: served by the streaming kernel for every size
+  if (!p1 && small_path(max_n, max_m, B, D)) {
     cudaError_t e = launch_small(prm, max_n, max_m, stream);
     if (e != cudaSuccess) return fail_cuda(e, "kdot_small_kernel");
     count_launches(1);
     return KDOT_OK;
   }
-  const size_t need = kdot_workspace_bytes(nimg, max_n, max_m, B, D);
+  const size_t need = kdot_workspace_bytes_ex(nimg, max_n, max_m, B, D, p);
   if (!workspace || workspace_bytes < need) return fail(KDOT_E_WORKSPACE, "workspace too small (see kdot_workspace_bytes)");
-  if (large_path(max_n, max_m, D) == 1) {
+  if (p1 || large_path(max_n, max_m, D) == 1) {
     cudaError_t e = launch_stream(prm, D, max_n, max_m, workspace, stream);
     if (e != cudaSuccess) return fail_cuda(e, "kdot_stream_kernel");
     count_launches(1);
@@ -330,7 +338,7 @@ int kdot_sinkhorn_fwd_bwd_host(kdot_host_ctx* c, float* xs_h, const float* ws_h,
   // transfer, small outputs written by the kernel straight into the mapped pinned staging area (posted PCIe writes;
   // removes the D2H copy-engine launch, ~8-10 us of fixed latency).  2: small problems also READ their inputs from the
   // mapped staging area (each element is read exactly once by the fused kernel), so the step is one kernel + one sync.
-  const bool small = small_path(max_n, max_m, B, D) && max_n + max_m <= 32;
+  const bool small = p == 2.0f && small_path(max_n, max_m, B, D) && max_n + max_m <= 32;
   const bool zc_out = c->zero_copy >= 1 && out_bytes <= (1u << 20) && !(normalize && write_back_normalized);
   const bool zc_in = c->zero_copy >= 2 && small && zc_out && in_bytes <= (1u << 20);
   char* in_base = zc_in ? c->pin_in_dev : c->dev_in;

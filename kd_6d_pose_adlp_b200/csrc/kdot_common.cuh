@@ -15,6 +15,7 @@ constexpr float kLogZeroWeight = -100000.0f;  // geomloss log_weights(): log(0) 
 
 // Per-round constants of the eps-scaling loop, derived in float64 and rounded once.
 //   v_ij (log2 domain) = h_j + coef * |x_i - y_j|^2          coef  = -0.5*log2(e)/eps      (p = 2)
+//                      = h_j + coef * |x_i - y_j|            coef  = -log2(e)/eps          (p = 1)
 //   new potential      = scale * log2-sum-exp                 scale = -lambda(eps)*eps*ln 2
 //   h_j for NEXT round = lw2_j + pot_j * hmul                 hmul  = log2(e)/eps_next
 struct RoundConst {
@@ -170,7 +171,7 @@ __device__ __forceinline__ RoundConst make_round_const(int r, const ImgSched& is
   const double eps_next = schedule_eps(round_to_sched(r + 1, is.nits), is, sp);
   const double lam = sp.rho < 0.0 ? 1.0 : 1.0 / (1.0 + eps / sp.rho);
   RoundConst rc;
-  rc.coef = (float)(-0.5 * 1.4426950408889634 / eps);
+  rc.coef = (float)((sp.p == 2.0 ? -0.5 : -1.0) * 1.4426950408889634 / eps);  // cost |d|^2/2 (p = 2) or |d| (p = 1)
   rc.scale = (float)(-lam * eps * 0.6931471805599453);
   rc.hmul = (float)(1.4426950408889634 / eps_next);
   rc.eps = (float)eps;

@@ -77,9 +77,19 @@ __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinter
 // FOLD is used only while the exponents are small (early, warm rounds: eps >= eps_0 / 256, |h| < ~200): there the
 // two extra roundings it introduces are < 2e-5.  In the cold rounds (|h| ~ 1e3..1e4) the unfolded form
 // (one rounding of v, then an exact subtraction) is kept, because those rounds set the accuracy of the result.
-template <int D, int R, bool GRAD, bool FOLD>
+// P1: cost |x - y| instead of |x - y|^2 / 2 (geomloss p = 1: sqrt(max(|d|^2, 1e-8)); the clamp also zeroes the
+// gradient there).  Never combined with FOLD.
+__device__ __forceinline__ float2 p1_norm(float2 q) {
+  return make_float2(sqrtf(fmaxf(q.x, 1e-8f)), sqrtf(fmaxf(q.y, 1e-8f)));
+}
+__device__ __forceinline__ float2 p1_grad_weight(float2 p, float2 q) {  // p / r, 0 where the clamp is active
+  return make_float2(q.x > 1e-8f ? p.x * rsqrtf(q.x) : 0.f, q.y > 1e-8f ? p.y * rsqrtf(q.y) : 0.f);
+}
+
+template <int D, int R, bool GRAD, bool FOLD, bool P1>
 __device__ __forceinline__ void stream_chunk(URow<D, R, GRAD> (&st)[R], const float4 (&X)[D], const float4& H,
                                              const float2 coef2, const float inv_ncoef, const float big) {
+  static_assert(!(FOLD && P1), "the folded form is only defined for the squared cost");
   float2 ps[R], p0s[GRAD ? R : 1], p1s[GRAD ? R : 1];
   bool rebase = false;
 #pragma unroll
@@ -93,6 +103,8 @@ __device__ __forceinline__ void stream_chunk(URow<D, R, GRAD> (&st)[R], const fl
       q0 = (!FOLD && d == 0) ? __fmul2_rn(a0, a0) : __ffma2_rn(a0, a0, q0);
       q1 = (!FOLD && d == 0) ? __fmul2_rn(a1, a1) : __ffma2_rn(a1, a1, q1);
     }
+    const float2 sq0 = q0, sq1 = q1;
+    if (P1) { q0 = p1_norm(q0); q1 = p1_norm(q1); }
     float2 e0 = __ffma2_rn(q0, coef2, make_float2(H.x, H.y));
     float2 e1 = __ffma2_rn(q1, coef2, make_float2(H.z, H.w));
     if (!FOLD) {
@@ -103,7 +115,7 @@ __device__ __forceinline__ void stream_chunk(URow<D, R, GRAD> (&st)[R], const fl
     const float2 p0 = make_float2(ex2_approx(e0.x), ex2_approx(e0.y));
     const float2 p1 = make_float2(ex2_approx(e1.x), ex2_approx(e1.y));
     ps[k] = __fadd2_rn(p0, p1);
-    if (GRAD) { p0s[k] = p0; p1s[k] = p1; }
+    if (GRAD) { p0s[k] = P1 ? p1_grad_weight(p0, sq0) : p0; p1s[k] = P1 ? p1_grad_weight(p1, sq1) : p1; }
     rebase |= !(ps[k].x + ps[k].y <= big);
   }
   if (rebase) {  // cold: exact max of the offending rows' chunk, re-base their running sums
@@ -119,6 +131,8 @@ __device__ __forceinline__ void stream_chunk(URow<D, R, GRAD> (&st)[R], const fl
         q0 = d == 0 ? __fmul2_rn(a0, a0) : __ffma2_rn(a0, a0, q0);
         q1 = d == 0 ? __fmul2_rn(a1, a1) : __ffma2_rn(a1, a1, q1);
       }
+      const float2 sq0 = q0, sq1 = q1;
+      if (P1) { q0 = p1_norm(q0); q1 = p1_norm(q1); }
       const float2 v0 = __ffma2_rn(q0, coef2, make_float2(H.x, H.y));
       const float2 v1 = __ffma2_rn(q1, coef2, make_float2(H.z, H.w));
       const float vm = fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y));
@@ -134,7 +148,7 @@ __device__ __forceinline__ void stream_chunk(URow<D, R, GRAD> (&st)[R], const fl
       const float2 p0 = make_float2(ex2_approx(v0.x - vm), ex2_approx(v0.y - vm));
       const float2 p1 = make_float2(ex2_approx(v1.x - vm), ex2_approx(v1.y - vm));
       ps[k] = __fadd2_rn(p0, p1);
-      if (GRAD) { p0s[k] = p0; p1s[k] = p1; }
+      if (GRAD) { p0s[k] = P1 ? p1_grad_weight(p0, sq0) : p0; p1s[k] = P1 ? p1_grad_weight(p1, sq1) : p1; }
     }
   }
 #pragma unroll
@@ -168,7 +182,7 @@ __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_g
 
 // R rows of this lane against columns [0, ncols) of one column set (ncols multiple of 4; SoA global arrays
 // pts[d][strideP], ch[]).  The h arrays are rewritten every round by other SMs: cp.async.cg reads them from L2.
-template <int D, int R, bool GRAD, bool FOLD>
+template <int D, int R, bool GRAD, bool FOLD, bool P1>
 __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const float* __restrict__ pts, int strideP,
                                             const float* ch, int ncols, float coef, float* wsm, int lane) {
   constexpr int T = stream_tile_cols<D>();
@@ -199,7 +213,7 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
 #pragma unroll
       for (int d = 0; d < D; ++d) X[d] = *reinterpret_cast<const float4*>(tb + d * T + j);
       const float4 H = *reinterpret_cast<const float4*>(tb + D * T + j);
-      stream_chunk<D, R, GRAD, FOLD>(st, X, H, coef2, inv_ncoef, big);
+      stream_chunk<D, R, GRAD, FOLD, P1>(st, X, H, coef2, inv_ncoef, big);
     }
     __syncwarp();  // every lane is done with this buffer before tile t+2 overwrites it
   }
@@ -223,7 +237,7 @@ __device__ __forceinline__ long long cell_index(const SinkhornParams& b, bool st
 }
 
 // One warp unit: rows [blk*32R, blk*32R + 32R) of one cloud of problem `prob` against one column set, round r.
-template <int D, int R>
+template <int D, int R, bool P1>
 __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int prob, int uu, int lane, float* wsm) {
   const SinkhornParams& b = p.b;
   const int B = b.B, strideP = p.strideP;
@@ -263,14 +277,14 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
       urow_reset<D, 1, true>(st, -1.0f / rc.coef);
 #pragma unroll
       for (int d = 0; d < D; ++d) st[0].nx[d] = -pts[(size_t)d * strideP + src];
-      stream_rows<D, 1, true, false>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane);
+      stream_rows<D, 1, true, false, P1>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane);
       const float sS = st[0].s.x + st[0].s.y;
       const float S = rc.scale * (st[0].mref + lg2_approx(sS));
       float gS[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) gS[d] = (st[0].g[d].x + st[0].g[d].y) / sS;
       urow_reset<D, 1, true>(st, -1.0f / rc.coef);
-      stream_rows<D, 1, true, false>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane);
+      stream_rows<D, 1, true, false, P1>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane);
       if (!act) continue;
       const float sC = st[0].s.x + st[0].s.y;
       const float C = rc.scale * (st[0].mref + lg2_approx(sC));
@@ -308,8 +322,8 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   }
   // warm rounds (eps >= eps_0 / 256): reference exponent folded into the distance chain (one op less per pair)
   const float eps0 = b.sched[(size_t)img * KDOT_MAX_ROUNDS].eps;
-  if (rc.eps * 256.0f >= eps0) stream_rows<D, R, false, true>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane);
-  else stream_rows<D, R, false, false>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane);
+  if (!P1 && rc.eps * 256.0f >= eps0) stream_rows<D, R, false, !P1, false>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane);
+  else stream_rows<D, R, false, false, P1>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane);
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     if (ridx[k] < 0) continue;
@@ -322,7 +336,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   }
 }
 
-template <int D, int R>
+template <int D, int R, bool P1>
 __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCKS : 2)) kdot_stream_kernel(StreamParams p) {
   cg::grid_group grid = cg::this_grid();
   const SinkhornParams& b = p.b;
@@ -487,7 +501,7 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
       }
       __syncwarp();
     }
-    stream_unit<D, R>(p, r, prob, uu, lane, wsm);
+    stream_unit<D, R, P1>(p, r, prob, uu, lane, wsm);
     __threadfence();
     __syncwarp();
     if (lane == 0) atomicAdd(p.done + prob, 1u);
@@ -560,20 +574,20 @@ size_t stream_workspace_bytes(int nimg, int max_n, int max_m, int B, int D) {
 
 bool stream_supports_dim(int D) { return D == 1 || D == 2 || D == 3 || D == 4 || D == 8 || D == 16; }
 
-template <int D, int R>
+template <int D, int R, bool P1 = false>
 static cudaError_t launch_stream_t(StreamParams& sp, cudaStream_t stream) {
   static int blocks_per_sm = 0, sms = 0;
   if (blocks_per_sm == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kdot_stream_kernel<D, R>, kStreamThreads,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kdot_stream_kernel<D, R, P1>, kStreamThreads,
                                                                   (kStreamThreads / 32) * stream_warp_smem_floats<D>() * sizeof(float));
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) return cudaErrorLaunchOutOfResources;
   }
   void* args[] = {&sp};
-  return cudaLaunchCooperativeKernel((const void*)kdot_stream_kernel<D, R>, dim3(blocks_per_sm * sms), dim3(kStreamThreads),
+  return cudaLaunchCooperativeKernel((const void*)kdot_stream_kernel<D, R, P1>, dim3(blocks_per_sm * sms), dim3(kStreamThreads),
                                      args, (kStreamThreads / 32) * stream_warp_smem_floats<D>() * sizeof(float), stream);
 }
 
@@ -593,6 +607,7 @@ cudaError_t launch_stream(const SinkhornParams& prm, int D, int max_n, int max_m
   sp.term = (float*)(base + pl.off_term);
   sp.ctr = (unsigned int*)(base + pl.off_ctr);
   sp.done = (unsigned int*)(base + pl.off_done);
+  if (prm.sp.p == 1.0) return D == 2 ? launch_stream_t<2, KDOT_STREAM_R2, true>(sp, stream) : cudaErrorInvalidValue;
   switch (D) {
     case 1: return launch_stream_t<1, KDOT_STREAM_R2>(sp, stream);
     case 2: return launch_stream_t<2, KDOT_STREAM_R2>(sp, stream);

@@ -111,7 +111,7 @@ def ot_loss_batched(xs, ws, xt, wt, pos_per_img, pos_per_img_t, cfg: OTConfig = 
         _lib.check(rc, "kdot_kernel_mmd_fwd_bwd")
         nits.zero_()
         return dict(loss_per_img=loss, loss_per_slot=slots, valid=valid, grad_xs=grad_xs, grad_ws=grad_ws, nits=nits)
-    ws_bytes = int(L.kdot_workspace_bytes(nimg, max_n, max_m, B, D))
+    ws_bytes = int(L.kdot_workspace_bytes_ex(nimg, max_n, max_m, B, D, float(cfg.p)))
     wsp = _workspace(dev, ws_bytes)
     with torch.cuda.device(dev):
         rc = L.kdot_sinkhorn_fwd_bwd(

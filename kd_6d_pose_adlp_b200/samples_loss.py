@@ -48,8 +48,8 @@ class SamplesLoss(torch.nn.Module):
         super().__init__()
         if loss not in ("sinkhorn", "gaussian", "laplacian", "energy"):
             raise NotImplementedError(f"SamplesLoss(loss={loss!r}): no CUDA kernel (sinkhorn, gaussian, laplacian, energy)")
-        if loss == "sinkhorn" and float(p) != 2.0:
-            raise NotImplementedError("SamplesLoss: only p=2 has a CUDA kernel")
+        if loss == "sinkhorn" and float(p) not in (1.0, 2.0):
+            raise NotImplementedError("SamplesLoss: p must be 1 or 2")
         if diameter is not None or cost is not None or kernel is not None or not debias or potentials:
             raise NotImplementedError("SamplesLoss: diameter/cost/kernel/debias=False/potentials are not supported")
         if backend not in ("auto", "tensorized"):

@@ -16,7 +16,7 @@ def test_samples_loss_rejects_what_has_no_kernel():
         SamplesLoss("l1")                       # --gtype l1 / l2 are not geomloss losses either
     assert SamplesLoss("gaussian", blur=0.05).config.loss == "gaussian"
     with pytest.raises(NotImplementedError):
-        SamplesLoss("sinkhorn", p=1)
+        SamplesLoss("sinkhorn", p=3)
     with pytest.raises(NotImplementedError):
         SamplesLoss("sinkhorn", p=2, debias=False)
     L = SamplesLoss("sinkhorn", p=2.0, blur=0.001, scaling=0.5, reach=0.5)

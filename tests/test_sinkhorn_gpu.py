@@ -129,8 +129,8 @@ def test_bad_arguments_fail_loudly():
     dev = torch.device("cuda:0")
     b = ot_batch(2, seed=0)
     t = {k: torch.from_numpy(b[k]).to(dev) for k in ("xs", "ws", "xt", "wt")}
-    with pytest.raises(_lib.KdotError, match="p == 2"):
-        ot_loss_batched(t["xs"], t["ws"], t["xt"], t["wt"], b["pos_per_img"], b["pos_per_img_t"], OTConfig(p=1.0))
+    with pytest.raises(_lib.KdotError, match="p must be 1 or 2"):
+        ot_loss_batched(t["xs"], t["ws"], t["xt"], t["wt"], b["pos_per_img"], b["pos_per_img_t"], OTConfig(p=3.0))
     with pytest.raises(ValueError):
         ot_loss_batched(t["xs"], t["ws"], t["xt"], t["wt"], b["pos_per_img"][:-1] + [999], b["pos_per_img_t"])
 
@@ -193,3 +193,35 @@ def test_stream_kernel_generic_dimension(D, blur):
             parity.report("grad_a", ad.grad.cpu().numpy(), res["ref32"][2], res["ref64"][2])]
     print("\n" + parity.fmt(rows))
     assert all(r["ok"] for r in rows), parity.fmt(rows)
+
+
+@pytest.mark.parametrize("blur,reach", [(0.01, 0.5), (0.05, None), (0.001, 0.5)])
+def test_p1_distance_cost(blur, reach):
+    """SamplesLoss("sinkhorn", p=1): cost |x - y| (geomloss distances with its 1e-8 clamp), streaming kernel."""
+    from kd_6d_pose_adlp_b200 import SamplesLoss
+    from oracle import geomloss_ref
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    for B, N, M in [(8, 10, 12), (2, 80, 60)]:
+        x = (0.5 + 0.05 * torch.randn(B, N, 2, generator=g)).float()
+        y = (0.5 + 0.05 * torch.randn(B, M, 2, generator=g)).float()
+        a = torch.rand(B, N, generator=g) * 0.9 + 0.05
+        b = torch.rand(B, M, generator=g) * 0.9 + 0.05
+        xd, ad = x.to(dev).requires_grad_(True), a.to(dev).requires_grad_(True)
+        L = SamplesLoss("sinkhorn", p=1, blur=blur, scaling=0.5, reach=reach)
+        out = L(ad, xd, b.to(dev), y.to(dev))
+        out.sum().backward()
+        refs = {}
+        for name, dt in (("ref32", torch.float32), ("ref64", torch.float64)):
+            xr, ar = x.clone().to(dt).requires_grad_(True), a.clone().to(dt).requires_grad_(True)
+            Lr = geomloss_ref.SamplesLoss("sinkhorn", p=1, blur=blur, scaling=0.5, reach=reach)
+            o = Lr(ar, xr, b.to(dt), y.to(dt))
+            o.sum().backward()
+            refs[name] = (o.detach().double().numpy(), xr.grad.double().numpy(), ar.grad.double().numpy(), Lr.last_nits)
+        assert int(L.last_nits.cpu()[0]) == refs["ref64"][3]
+        rows = [parity.report("loss", out.detach().cpu().numpy(), refs["ref32"][0], refs["ref64"][0]),
+                parity.report("grad_x", xd.grad.cpu().numpy(), refs["ref32"][1], refs["ref64"][1]),
+                parity.report("grad_a", ad.grad.cpu().numpy(), refs["ref32"][2], refs["ref64"][2])]
+        print("\n" + parity.fmt(rows))
+        assert all(r["ok"] for r in rows), parity.fmt(rows)
