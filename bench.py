@@ -45,14 +45,23 @@ WORKLOADS = {
     # BASELINE.json configs[2] variant 3b: every cell of the darknet_tiny / darknet53 grids
     "dense_b32": dict(nimg=32, dense=(1360, 1364), desc="all cells: N=1360 student / M=1364 teacher cells per "
                       "image, B=8, D=2, batch 32 per GPU"),
+    # BASELINE.json configs[3]: dense ZebraPose-style 16-D per-cell code distributions on a 64x64 grid, one slot
+    "zebra_b8": dict(nimg=8, dense=(4096, 4096), B=1, D=16, blur=0.05, desc="ZebraPose-style: N=M=4096 cells (64x64 "
+                     "grid), D=16 code probabilities, B=1, blur=0.05, batch 8 per GPU"),
 }
+
+
+def workload_cfg(workload):
+    w = WORKLOADS[workload]
+    return dict(CFG, blur=w.get("blur", CFG["blur"]))
 
 
 def make_batch(workload, rank, nimg=None):
     from kd_6d_pose_adlp_b200.synthetic import ot_batch
 
     w = WORKLOADS[workload]
-    return ot_batch(nimg or w["nimg"], seed=1234 + rank, dense=w["dense"], sigma=0.05 if w["dense"] is None else 0.1)
+    return ot_batch(nimg or w["nimg"], seed=1234 + rank, dense=w["dense"], sigma=0.05 if w["dense"] is None else 0.1,
+                    B=w.get("B", 8), D=w.get("D", 2))
 
 
 def algorithmic_work(batch, nits):
@@ -199,8 +208,10 @@ def run_reference_arm(args, rank, world):
 class DeviceBench:
     """Device-resident runner: preallocated buffers, direct C-ABI calls on the current stream."""
 
-    def __init__(self, batch, dev):
+    def __init__(self, batch, dev, cfg=None):
         import torch
+
+        self.cfg = cfg or CFG
 
         from kd_6d_pose_adlp_b200 import _lib
         from kd_6d_pose_adlp_b200.ops import cu_seqlens
@@ -239,8 +250,9 @@ class DeviceBench:
         torch = self.torch
         rc = self.L.kdot_sinkhorn_fwd_bwd(
             self.xs.data_ptr(), self.ws.data_ptr(), self.xt.data_ptr(), self.wt.data_ptr(), self.cu_n.data_ptr(),
-            self.cu_m.data_ptr(), self.nimg, self.B, self.D, self.max_n, self.max_m, 0, CFG["p"], CFG["blur"],
-            CFG["reach"], CFG["scaling"], CFG["w"], CFG["h"], 1, self.loss.data_ptr(), None, self.valid.data_ptr(),
+            self.cu_m.data_ptr(), self.nimg, self.B, self.D, self.max_n, self.max_m, 0, self.cfg["p"], self.cfg["blur"],
+            self.cfg["reach"], self.cfg["scaling"], self.cfg["w"], self.cfg["h"], 1 if self.D == 2 else 0,
+            self.loss.data_ptr(), None, self.valid.data_ptr(),
             self.gx.data_ptr(), self.gw.data_ptr(), self.nits.data_ptr(), self.wsp.data_ptr(), self.wsp_bytes,
             torch.cuda.current_stream(self.dev).cuda_stream)
         self._lib.check(rc, "kdot_sinkhorn_fwd_bwd")
@@ -266,7 +278,7 @@ class DeviceBench:
         return sum(per), per, launches
 
 
-def host_e2e(batch, dev_index, steps, warmup, barrier):
+def host_e2e(batch, dev_index, steps, warmup, barrier, cfg=CFG):
     """End to end through kdot_sinkhorn_fwd_bwd_host: host numpy buffers in, host numpy buffers out."""
     from kd_6d_pose_adlp_b200 import _lib
 
@@ -287,12 +299,16 @@ def host_e2e(batch, dev_index, steps, warmup, barrier):
     gx = np.empty_like(xs)
     gw = np.empty_like(ws)
     p = lambda a: a.ctypes.data
+    normalize = 1 if D == 2 else 0
+    # raw host addresses of the caller's NumPy buffers, taken once (as any caller holding fixed buffers would)
+    args = (ctx, p(xs), p(ws), p(xt), p(wt), p(pn), p(pm), nimg, cfg["p"], cfg["blur"], cfg["reach"], cfg["scaling"],
+            cfg["w"], cfg["h"], normalize, 0, p(loss), p(valid), p(gx), p(gw), p(nits))
+    call = L.kdot_sinkhorn_fwd_bwd_host
 
     def step():
-        rc = L.kdot_sinkhorn_fwd_bwd_host(ctx, p(xs), p(ws), p(xt), p(wt), p(pn), p(pm), nimg, CFG["p"], CFG["blur"],
-                                          CFG["reach"], CFG["scaling"], CFG["w"], CFG["h"], 1, 0, p(loss), p(valid),
-                                          p(gx), p(gw), p(nits))
-        _lib.check(rc, "kdot_sinkhorn_fwd_bwd_host")
+        rc = call(*args)
+        if rc != 0:
+            _lib.check(rc, "kdot_sinkhorn_fwd_bwd_host")
 
     for _ in range(warmup):
         step()
@@ -321,10 +337,11 @@ def kernel_name(max_n, max_m, launches_per_step):
     return "kdot_tiled_kernel" if launches_per_step == 2 else "kdot_stream_kernel"
 
 
-def ncu_traffic_bytes(kernel):
+def ncu_traffic_bytes(kernel, workload):
     """DRAM bytes (read + write) of one launch of `kernel` from the committed `ncu --set full` summary of the same
-    workload (profiles/r01_prof_*_ncu_summary.txt), or None when no capture is on file."""
-    tag = {"kdot_small_fast_kernel": "small_fast", "kdot_stream_kernel": "stream", "kdot_tiled_kernel": "tiled"}.get(kernel)
+    workload (profiles/r01_prof_*_ncu_summary.txt), or None when no capture of that kernel ON THAT WORKLOAD is on file."""
+    tag = {("kdot_small_fast_kernel", "ape_b64"): "small_fast", ("kdot_stream_kernel", "dense_b32"): "stream",
+           ("kdot_tiled_kernel", "dense_b32"): "tiled"}.get((kernel, workload))
     path = os.path.join(ROOT, "profiles", f"r01_prof_{tag}_ncu_summary.txt")
     if tag is None or not os.path.exists(path):
         return None
@@ -393,8 +410,9 @@ def main():
     fp32_peak = float(L.kdot_measure_fp32_peak_tflops(local_rank, 2000))
 
     batch = make_batch(args.workload, rank)
+    cfg = workload_cfg(args.workload)
     nimg = len(batch["pos_per_img"])
-    bench = DeviceBench(batch, dev)
+    bench = DeviceBench(batch, dev, cfg)
     sampler = ClockSampler(local_rank)
     sampler.start()
     total_ms, per, launches = bench.timed(args.steps, args.warmup, barrier)
@@ -416,13 +434,16 @@ def main():
         "hbm": {"achieved": byts / (ms_per_step * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                 "frac": byts / (ms_per_step * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6552.0), "peak_source": peak_src},
         "algorithmic_flops_per_step": flops, "algorithmic_bytes_per_step": byts, "median_ms_per_step": med_ms,
+        "note": ("ape-shaped problems are ~20 x 20 points: the launch is bound by the latency of its dependent Sinkhorn "
+                 "rounds, not by a pipe; see the `dense` object for the roofline-relevant configuration")
+        if args.workload == "ape_b64" else None,
     }
 
-    roofline["traffic"] = ncu_traffic_bytes(roofline["kernel"])
+    roofline["traffic"] = ncu_traffic_bytes(roofline["kernel"], args.workload)
     roofline["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/)"
 
     # end to end through the host-buffer C-ABI call
-    e2e_dt, h2d, d2h, mean_loss = host_e2e(batch, local_rank, args.steps, args.warmup, barrier)
+    e2e_dt, h2d, d2h, mean_loss = host_e2e(batch, local_rank, args.steps, args.warmup, barrier, cfg)
     e2e_dt = max_over_ranks(e2e_dt)
     e2e = {"value": nimg * world * args.steps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_dt / args.steps * 1e3, "mean_kd_loss": mean_loss,
@@ -434,7 +455,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "images_per_gpu": nimg,
                    "l2": "256 MiB buffer written between timed steps (L2 flush), inputs restored outside the events",
-                   "parallelism": f"images sharded over {world} rank(s), no data-path collective", **CFG},
+                   "parallelism": f"images sharded over {world} rank(s), no data-path collective", **cfg},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
 
@@ -450,13 +471,13 @@ def main():
             "roofline": {"bound": "fp32", "kernel": kernel_name(dbench.max_n, dbench.max_m, d_launch // 3), "achieved": d_fl / (d_ms * 1e-3) / 1e12,
                          "peak": fp32_peak, "unit": "TFLOP/s", "frac": d_fl / (d_ms * 1e-3) / 1e12 / fp32_peak,
                          "sfu_exp_per_s": d_ex / (d_ms * 1e-3),
-                         "traffic": ncu_traffic_bytes(kernel_name(dbench.max_n, dbench.max_m, d_launch // 3)),
+                         "traffic": ncu_traffic_bytes(kernel_name(dbench.max_n, dbench.max_m, d_launch // 3), "dense_b32"),
                          "algorithmic_bytes_per_step": d_by,
                          "hbm_gbs": d_by / (d_ms * 1e-3) / 1e9},
         }
         del dbench
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and batch["xs"].shape[1] == 8:
         v, passes, dt, cores = cpu_port_images_per_sec(batch, threads=len(os.sched_getaffinity(0)))
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{passes} passes over the {nimg}-image {args.workload} batch in {dt:.1f} s "
