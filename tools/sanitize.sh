@@ -1,0 +1,35 @@
+#!/bin/bash
+# compute-sanitizer passes over every kernel family (run on the GPU box); summaries -> gpurun_out/
+R=${1:-r01}
+mkdir -p gpurun_out
+cat > /tmp/kdot_sanitize_drive.py <<'PY'
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.getcwd())
+from kd_6d_pose_adlp_b200.ops import OTConfig, ot_loss_batched
+from kd_6d_pose_adlp_b200.synthetic import ot_batch
+from kd_6d_pose_adlp_b200 import SamplesLoss
+dev = torch.device("cuda:0")
+def run(b, cfg=OTConfig(), **kw):
+    t = {k: torch.from_numpy(b[k]).to(dev) for k in ("xs", "ws", "xt", "wt")}
+    o = ot_loss_batched(t["xs"], t["ws"], t["xt"], t["wt"], b["pos_per_img"], b["pos_per_img_t"], cfg, **kw)
+    torch.cuda.synchronize(); return float(o["loss_per_img"].sum())
+print("small fast", run(ot_batch(6, seed=1, p_empty_teacher=0.3)))
+print("small general", run(ot_batch(3, seed=2, n_range=(20, 30), m_range=(20, 30))))
+print("stream", run(ot_batch(3, seed=3, n_range=(40, 90), m_range=(40, 90), p_empty_teacher=0.3)))
+os.environ["KDOT_FORCE_PATH"] = "tiled"
+print("tiled", run(ot_batch(2, seed=4, n_range=(40, 90), m_range=(40, 90))))
+os.environ.pop("KDOT_FORCE_PATH")
+print("mmd", run(ot_batch(3, seed=5), OTConfig(loss="energy", blur=0.05)))
+print("p1", run(ot_batch(2, seed=6), OTConfig(p=1.0, blur=0.01)))
+x = torch.sigmoid(torch.randn(1, 60, 16)).to(dev); y = torch.sigmoid(torch.randn(1, 50, 16)).to(dev)
+print("stream D=16", float(SamplesLoss("sinkhorn", p=2, blur=0.05)(x, y).sum()))
+from kd_6d_pose_adlp_b200.postprocess.postprocess_kd import select_cells
+cls = [torch.randn(2, 15, h, h, device=dev) - 2 for h in (32, 16, 8, 4, 2)]
+reg = [torch.randn(2, 240, h, h, device=dev) * 0.3 for h in (32, 16, 8, 4, 2)]
+s = select_cells(cls, reg, [32, 64, 128, 256, 512], [8, 16, 32, 64, 128], 0.1, 10, 1.0); torch.cuda.synchronize()
+print("select", int(s["sel_count"].sum()))
+PY
+for tool in memcheck racecheck synccheck; do
+  timeout 900 compute-sanitizer --tool $tool --print-limit 5 python /tmp/kdot_sanitize_drive.py > gpurun_out/${R}_sanitizer_${tool}.txt 2>&1
+  echo "== $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/${R}_sanitizer_${tool}.txt | tail -1)"
+done
