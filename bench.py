@@ -51,9 +51,16 @@ WORKLOADS = {
 }
 
 
-def workload_cfg(workload):
+def workload_cfg(workload, args=None):
+    """Solver knobs of a workload; ``--scaling`` / ``--blur`` override them (BASELINE.json configs[4]: the
+    iteration / epsilon sweep)."""
     w = WORKLOADS[workload]
-    return dict(CFG, blur=w.get("blur", CFG["blur"]))
+    cfg = dict(CFG, blur=w.get("blur", CFG["blur"]))
+    if args is not None and args.scaling is not None:
+        cfg["scaling"] = args.scaling
+    if args is not None and args.blur is not None:
+        cfg["blur"] = args.blur
+    return cfg
 
 
 def make_batch(workload, rank, nimg=None):
@@ -124,27 +131,54 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_port_images_per_sec(batch, budget_s=12.0, min_passes=2, threads=None):
-    """Times the oracle port of the reference formulation (fp32 torch CPU ops + autograd) on `batch`."""
+def cpu_step_fn(batch, cfg):
+    """One fwd+bwd pass of the reference formulation on host cores (oracle port: fp32 torch CPU ops + autograd).
+    D == 2 goes through the restated ``kd_loss_2d`` driver (normalise, per-image loop, transposes); other D call the
+    restated ``SamplesLoss`` once per image on the ``(B, N, D)`` layout."""
     import torch
 
-    from oracle import geomloss_ref, kd_loss_ref  # test infrastructure: allowed here (cpu_baseline leg only)
+    from oracle import geomloss_ref, kd_loss_ref  # test infrastructure: allowed in the cpu_baseline / reference legs only
+
+    L = geomloss_ref.SamplesLoss("sinkhorn", p=cfg["p"], blur=cfg["blur"], scaling=cfg["scaling"], reach=cfg["reach"])
+    B, D = batch["xs"].shape[1], batch["xs"].shape[2]
+    pn, pm = batch["pos_per_img"], batch["pos_per_img_t"]
+    wt = torch.from_numpy(batch["wt"])
+    if D == 2 and B == 8:
+        xt0 = torch.from_numpy(batch["xt"].reshape(-1, 2))
+
+        def one_pass():
+            xs = torch.from_numpy(batch["xs"].reshape(-1, 2)).clone().requires_grad_(True)
+            ws = torch.from_numpy(batch["ws"]).clone().requires_grad_(True)
+            losses = kd_loss_ref.kd_loss_2d_ref(xs.clone(), xt0.clone(), ws, wt, cfg["w"], cfg["h"], "point", L, dim=2,
+                                                pos_per_img=pn, pos_per_img_t=pm)
+            (sum(losses) / len(losses)).backward()
+            return xs.grad
+    else:
+        xt0 = torch.from_numpy(batch["xt"])
+
+        def one_pass():
+            xs = torch.from_numpy(batch["xs"]).clone().requires_grad_(True)
+            ws = torch.from_numpy(batch["ws"]).clone().requires_grad_(True)
+            losses, s0, t0 = [], 0, 0
+            for n, m in zip(pn, pm):
+                if n > 0 and m > 0:
+                    losses.append(L(ws[s0:s0 + n].transpose(0, 1).contiguous(), xs[s0:s0 + n].transpose(0, 1).contiguous(),
+                                    wt[t0:t0 + m].transpose(0, 1).contiguous(),
+                                    xt0[t0:t0 + m].transpose(0, 1).contiguous()).sum())
+                s0, t0 = s0 + n, t0 + m
+            (sum(losses) / len(losses)).backward()
+            return xs.grad
+    return one_pass
+
+
+def cpu_port_images_per_sec(batch, cfg, budget_s=12.0, min_passes=2, threads=None):
+    """Times the oracle port of the reference formulation on `batch` for about `budget_s` seconds."""
+    import torch
 
     if threads:
         torch.set_num_threads(threads)
-    L = geomloss_ref.SamplesLoss("sinkhorn", p=CFG["p"], blur=CFG["blur"], scaling=CFG["scaling"], reach=CFG["reach"])
-    xt0 = torch.from_numpy(batch["xt"].reshape(-1, 2))
-    wt = torch.from_numpy(batch["wt"])
+    one_pass = cpu_step_fn(batch, cfg)
     nimg = len(batch["pos_per_img"])
-
-    def one_pass():
-        xs = torch.from_numpy(batch["xs"].reshape(-1, 2)).clone().requires_grad_(True)
-        ws = torch.from_numpy(batch["ws"]).clone().requires_grad_(True)
-        losses = kd_loss_ref.kd_loss_2d_ref(xs.clone(), xt0.clone(), ws, wt, CFG["w"], CFG["h"], "point", L, dim=2,
-                                            pos_per_img=batch["pos_per_img"], pos_per_img_t=batch["pos_per_img_t"])
-        (sum(losses) / len(losses)).backward()
-        return xs.grad
-
     one_pass()  # warm-up
     t0 = time.perf_counter()
     passes = 0
@@ -159,29 +193,18 @@ def cpu_port_images_per_sec(batch, budget_s=12.0, min_passes=2, threads=None):
 
 def run_reference_arm(args, rank, world):
     """--impl reference: the reference's formulation on the box's host cores (oracle port; geomloss itself is
-    not installable offline).  Rank 0 only."""
+    not installable offline).  Rank 0 only; each step is a bounded sample of the workload."""
     if rank != 0:
         return
     import torch
 
     workload = args.workload
-    sample_img = 64 if WORKLOADS[workload]["dense"] is None else 1
+    cfg = workload_cfg(workload, args)
+    sample_img = min(args.images or 64, 64) if WORKLOADS[workload]["dense"] is None else 1
     batch = make_batch(workload, 0, nimg=sample_img)
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    from oracle import geomloss_ref, kd_loss_ref
-
-    L = geomloss_ref.SamplesLoss("sinkhorn", p=CFG["p"], blur=CFG["blur"], scaling=CFG["scaling"], reach=CFG["reach"])
-    xt0 = torch.from_numpy(batch["xt"].reshape(-1, 2))
-    wt = torch.from_numpy(batch["wt"])
-
-    def step():
-        xs = torch.from_numpy(batch["xs"].reshape(-1, 2)).clone().requires_grad_(True)
-        ws = torch.from_numpy(batch["ws"]).clone().requires_grad_(True)
-        losses = kd_loss_ref.kd_loss_2d_ref(xs.clone(), xt0.clone(), ws, wt, CFG["w"], CFG["h"], "point", L, dim=2,
-                                            pos_per_img=batch["pos_per_img"], pos_per_img_t=batch["pos_per_img_t"])
-        (sum(losses) / len(losses)).backward()
-
+    step = cpu_step_fn(batch, cfg)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -195,7 +218,7 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "desc": WORKLOADS[workload]["desc"], **CFG},
+        "config": {"workload": workload, "desc": WORKLOADS[workload]["desc"], **cfg},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -369,6 +392,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="kdot", choices=["kdot", "reference"])
     ap.add_argument("--workload", default="ape_b64", choices=sorted(WORKLOADS))
+    ap.add_argument("--images", type=int, default=None, help="images per GPU (default: the workload's batch)")
+    ap.add_argument("--scaling", type=float, default=None, help="override the epsilon-scaling ratio (iteration sweep)")
+    ap.add_argument("--blur", type=float, default=None, help="override the blur (final temperature = blur**p)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the secondary dense-workload roofline leg")
     args = ap.parse_args()
@@ -409,8 +435,8 @@ def main():
     peaks, peak_src = measured_peaks()
     fp32_peak = float(L.kdot_measure_fp32_peak_tflops(local_rank, 2000))
 
-    batch = make_batch(args.workload, rank)
-    cfg = workload_cfg(args.workload)
+    batch = make_batch(args.workload, rank, nimg=args.images)
+    cfg = workload_cfg(args.workload, args)
     nimg = len(batch["pos_per_img"])
     bench = DeviceBench(batch, dev, cfg)
     sampler = ClockSampler(local_rank)
@@ -455,7 +481,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "images_per_gpu": nimg,
                    "l2": "256 MiB buffer written between timed steps (L2 flush), inputs restored outside the events",
-                   "parallelism": f"images sharded over {world} rank(s), no data-path collective", **cfg},
+                   "parallelism": f"images sharded over {world} rank(s), no data-path collective",
+                   "softmin_rounds_per_image": int(np.median(nits[nits > 0])) + 2 if (nits > 0).any() else 0, **cfg},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
 
@@ -477,10 +504,12 @@ def main():
         }
         del dbench
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and batch["xs"].shape[1] == 8:
-        v, passes, dt, cores = cpu_port_images_per_sec(batch, threads=len(os.sched_getaffinity(0)))
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = batch if WORKLOADS[args.workload]["dense"] is None else make_batch(args.workload, 0, nimg=1)
+        v, passes, dt, cores = cpu_port_images_per_sec(cb, cfg, threads=len(os.sched_getaffinity(0)),
+                                                       min_passes=1 if cb is not batch else 2)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{passes} passes over the {nimg}-image {args.workload} batch in {dt:.1f} s "
+                                "sample": f"{passes} passes over a {len(cb['pos_per_img'])}-image {args.workload} batch in {dt:.1f} s "
                                           "(fp32 torch CPU ops + autograd: the reference formulation)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
