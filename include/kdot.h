@@ -161,6 +161,31 @@ int kdot_select_cells(const float* const* cls_lvl, const float* const* reg_lvl, 
                       float* sel_kpts, int32_t* nk, int32_t* valid_cnt, int32_t* best,
                       void* cuda_stream);
 
+/*
+ * Student-side prologue / epilogue of the loss: gather the 16 key-point
+ * offsets of every positive cell straight from the per-level head outputs and decode them to full-image
+ * pixels, and the transposed scatter for the backward pass.  Replaces
+ *   flatten of pred_reg                    (losses/loss.py:62-96; permute + reshape + cat of ~83 MB at batch 64)
+ *   pred_reg_flatten[pos_inds]             (losses/kd_loss.py:156)
+ *   pred.view(n,-1,16)[arange(n), cls]     (losses/kd_loss.py:47)
+ *   TargetCoder.decode                     (models/model.py:144-166: offset * anchor size + centre, inverse crop affine)
+ *   .view(-1,2,8).transpose(1,2)           (losses/kd_loss.py:50)
+ * and their autograd backward.
+ *
+ * reg_lvl[l] -> (nimg, C*16, H_l, W_l) fp32 device tensors (host array of device pointers), hw_lvl[l] = H_l*W_l
+ * (host); pos_inds[npos] int64 flat cell indices img*cells + level_offset + h*W + w (the reference's label
+ * order); cls_label[npos] int64 0-based class per cell; anchors[npos][4] xyxy of those cells;
+ * bbox_trans[npos][2][3] crop affines or NULL.  Forward writes xy[npos][8][2] (key-point k: x, y).
+ * Backward takes g_xy[npos][8][2] and writes d/d(offset) at the same 16 addresses of g_reg_lvl[l], which the
+ * caller has zero-filled (pos_inds are unique, so there are no atomics).
+ */
+int kdot_gather_decode_fwd(const float* const* reg_lvl, const int32_t* hw_lvl, int nlvl, int nimg, int C,
+                           const int64_t* pos_inds, const int64_t* cls_label, const float* anchors,
+                           const float* bbox_trans, int npos, float* xy, void* cuda_stream);
+int kdot_gather_decode_bwd(const float* g_xy, const int32_t* hw_lvl, int nlvl, int nimg, int C,
+                           const int64_t* pos_inds, const int64_t* cls_label, const float* anchors,
+                           const float* bbox_trans, int npos, float* const* g_reg_lvl, void* cuda_stream);
+
 /* Diagnostics */
 const char* kdot_last_error(void);
 int kdot_version(void);

@@ -18,7 +18,7 @@ KDOT_MAX_ROUNDS = 1024
 # every symbol include/kdot.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = (
     "kdot_sinkhorn_fwd_bwd", "kdot_kernel_mmd_fwd_bwd", "kdot_workspace_bytes", "kdot_workspace_bytes_ex", "kdot_host_ctx_create", "kdot_host_ctx_destroy",
-    "kdot_sinkhorn_fwd_bwd_host", "kdot_host_ctx_last_traffic", "kdot_host_ctx_last_timing", "kdot_select_cells", "kdot_last_error",
+    "kdot_sinkhorn_fwd_bwd_host", "kdot_host_ctx_last_traffic", "kdot_host_ctx_last_timing", "kdot_select_cells", "kdot_gather_decode_fwd", "kdot_gather_decode_bwd", "kdot_last_error",
     "kdot_version", "kdot_launch_count", "kdot_measure_fp32_peak_tflops", "kdot_debug_set_clock_buffer",
 )
 
@@ -66,6 +66,10 @@ def lib():
     L.kdot_select_cells.argtypes = (
         [vp] * 5 + [i32, vp, i32, i32, i32, f32, i32, f32, i32] + [vp] * 8 + [vp]
     )
+    L.kdot_gather_decode_fwd.restype = i32
+    L.kdot_gather_decode_fwd.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]
+    L.kdot_gather_decode_bwd.restype = i32
+    L.kdot_gather_decode_bwd.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]
     L.kdot_debug_set_clock_buffer.argtypes = [vp]
     L.kdot_measure_fp32_peak_tflops.restype = C.c_double
     L.kdot_measure_fp32_peak_tflops.argtypes = [i32, i32]

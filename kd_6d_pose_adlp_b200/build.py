@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libkdot.so")
 STAMP = os.path.join(LIB_DIR, "libkdot.stamp")
-SOURCES = ["kdot_api.cu", "kdot_small.cu", "kdot_tiled.cu", "kdot_stream.cu", "kdot_mmd.cu", "kdot_select.cu"]
+SOURCES = ["kdot_api.cu", "kdot_small.cu", "kdot_tiled.cu", "kdot_stream.cu", "kdot_mmd.cu", "kdot_select.cu", "kdot_decode.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v",

@@ -15,27 +15,27 @@ from __future__ import annotations
 
 import os
 
+import numpy as np
 import torch
 from torch import nn
 
-from ..ops import OTLossFunction
+from ..ops import OTLossFunction, gather_decode
 from ..samples_loss import SamplesLoss
 
 INF = 100000000
+
+
+def flatten_level_list(levels):
+    """One head output, per-level ``(nimg, C, H, W)`` -> ``(nimg*cells, C)`` in the same label order."""
+    parts = [t.permute(0, 2, 3, 1).reshape(t.shape[0], -1, t.shape[1]) for t in levels]
+    return (parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)).reshape(-1, parts[0].shape[2])
 
 
 def flatten_head_outputs(pred_cls, pred_reg):
     """Per-level ``(nimg, C, H, W)`` / ``(nimg, C*16, H, W)`` -> ``(nimg*cells, C)`` / ``(nimg*cells, C*16)``
     in the label order of the reference (``losses/loss.py:62-96``): image-major, levels concatenated,
     row-major cells."""
-    cls_l, reg_l = [], []
-    for c, r in zip(pred_cls, pred_reg):
-        n = c.shape[0]
-        cls_l.append(c.permute(0, 2, 3, 1).reshape(n, -1, c.shape[1]))
-        reg_l.append(r.permute(0, 2, 3, 1).reshape(n, -1, r.shape[1]))
-    n_cls, n_reg = cls_l[0].shape[2], reg_l[0].shape[2]
-    cls_f = (cls_l[0] if len(cls_l) == 1 else torch.cat(cls_l, dim=1)).reshape(-1, n_cls)
-    reg_f = (reg_l[0] if len(reg_l) == 1 else torch.cat(reg_l, dim=1)).reshape(-1, n_reg)
+    cls_f, reg_f = flatten_level_list(pred_cls), flatten_level_list(pred_reg)
     return cls_f, reg_f
 
 
@@ -97,6 +97,11 @@ def make_kd_pose_loss(base):
             picked = pred.view(n_cell, -1, 16)[torch.arange(n_cell, device=pred.device), cls_labels]
             pred_xy = self.target_coder.decode(picked, anchors, bbox_trans)
             pred_xy = pred_xy.view(-1, 2, 8).transpose(1, 2).contiguous().view(-1, 2)  # (cells*8, 2) px
+            return self._losses_from_keypoints(pred_xy, target_3D_in_camera_frame, cls_labels, pred_t, weight)
+
+        def _losses_from_keypoints(self, pred_xy, target_3D_in_camera_frame, cls_labels, pred_t, weight=None):
+            """Everything of ``KDObjectSpaceLoss`` after the decode (``kd_loss.py:52-103``): 3-D regression loss and
+            the OT distillation loss on ``pred_xy (cells*8, 2)`` pixel key-points."""
             losses = self._object_space_reg_loss(pred_xy, target_3D_in_camera_frame, cls_labels)
 
             # ---- OT distillation (kd_loss.py:73-103), one fused launch for the mini-batch ----
@@ -141,16 +146,21 @@ def make_kd_pose_loss(base):
             self.h = 480  # full-image size, not the 256 crop (kd_loss.py:116-117)
             self.w = 640
 
-            pred_cls_flat, pred_reg_flat = flatten_head_outputs(pred_cls, pred_reg)
+            # only the class logits are flattened (the focal loss reads every cell); the 240-channel regression maps
+            # are read in place by the gather/decode kernel at the positive cells -- the reference's flatten of
+            # pred_reg (losses/loss.py:62-96) is ~83 MB of copies per direction at batch 64 for ~640 used rows
+            pred_cls_flat = flatten_level_list(pred_cls)
             labels_flat = torch.cat(labels, dim=0)
-            reg_targets_flat = torch.cat(reg_targets, dim=0)
             aux_3d_flat = torch.cat(aux_3d, dim=0)
             anchors_flat = self._flatten_anchors(anchors)
             bbox_trans_flat = torch.cat(aux_bbox_trans, dim=0)
 
             pos_inds = torch.nonzero(labels_flat > 0).squeeze(1)
-            # one host sync for all per-image positive counts (the reference pays nimg + 1 `.item()` calls)
-            pos_per_img = torch.stack([(lb > 0).sum() for lb in labels]).tolist()
+            # all per-image positive counts from one prefix sum and ONE host sync (the reference pays nimg + 1
+            # `.item()` calls, kd_loss.py:131,145)
+            ends = np.cumsum([int(lb.shape[0]) for lb in labels])
+            at_ends = torch.cumsum(labels_flat > 0, dim=0)[torch.from_numpy(ends - 1).to(labels_flat.device)]
+            pos_per_img = np.diff(at_ends.cpu().numpy(), prepend=0).tolist()
             total_num_pos = _reduce_sum_int(int(sum(pos_per_img)), labels_flat.device)
 
             valid_inds = torch.nonzero(labels_flat >= 0).squeeze(1)
@@ -165,12 +175,14 @@ def make_kd_pose_loss(base):
                     raise NotImplementedError("KDPoseLoss: only LOSS_REG_TYPE == '3D' carries the KD loss (kd_loss.py:150-153)")
                 if self.weighted_ot:
                     self.pred_cls = torch.clamp(torch.sigmoid(pred_cls_flat[pos_inds]), min=10e-4, max=1 - 10e-4)
-                reg_loss, kd_loss = self.KDObjectSpaceLoss(
-                    pred_reg_flat[pos_inds], reg_targets_flat[pos_inds], aux_3d_flat[pos_inds], cls_label,
-                    anchors_flat[pos_inds], pred_t, bbox_trans_flat[pos_inds])
+                if getattr(self.target_coder, "regression_type", "POINT") != "POINT":
+                    raise NotImplementedError("KDPoseLoss: only the 'POINT' regression type is defined (models/model.py:145,163)")
+                self.cls_id = torch.unique(cls_label)
+                pred_xy = gather_decode(pred_reg, pos_inds, cls_label, anchors_flat[pos_inds], bbox_trans_flat[pos_inds])
+                reg_loss, kd_loss = self._losses_from_keypoints(pred_xy, aux_3d_flat[pos_inds], cls_label, pred_t)
             else:
-                reg_loss = pred_reg_flat.sum()
-                kd_loss = pred_reg_flat.sum()
+                reg_loss = sum(r.sum() for r in pred_reg)  # == pred_reg_flatten.sum() (kd_loss.py:158-159)
+                kd_loss = reg_loss
             if hasattr(self, "step"):
                 self.step += 1
             return [cls_loss, reg_loss, kd_loss]
@@ -178,10 +190,7 @@ def make_kd_pose_loss(base):
         @staticmethod
         def _flatten_anchors(anchors):
             """``anchors``: per image, per level BoxList-like objects with ``.bbox`` (or plain tensors)."""
-            per_img = []
-            for levels in anchors:
-                per_img.append(torch.cat([a.bbox if hasattr(a, "bbox") else a for a in levels], dim=0))
-            return torch.cat(per_img, dim=0)
+            return torch.cat([a.bbox if hasattr(a, "bbox") else a for levels in anchors for a in levels], dim=0)
 
     KDPoseLoss.__qualname__ = "KDPoseLoss"
     return KDPoseLoss

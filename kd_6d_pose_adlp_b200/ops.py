@@ -7,6 +7,7 @@ the autograd graph only -- all arithmetic runs in ``libkdot.so``.
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -88,18 +89,26 @@ def ot_loss_batched(xs, ws, xt, wt, pos_per_img, pos_per_img_t, cfg: OTConfig = 
     if sum(pos_per_img) != sum_n or sum(pos_per_img_t) != sum_m:
         raise ValueError("per-image cell counts do not add up to the number of cells")
     dev = xs.device
-    if cu_n is None:
-        cu_n = cu_seqlens(pos_per_img, dev)
-    if cu_m is None:
-        cu_m = cu_seqlens(pos_per_img_t, dev)
+    if cu_n is None or cu_m is None:
+        # both prefix-sum arrays travel in ONE small H2D copy
+        cu = np.zeros(2 * (nimg + 1), np.int32)
+        np.cumsum(np.asarray(pos_per_img, np.int64), out=cu[1:nimg + 1])
+        np.cumsum(np.asarray(pos_per_img_t, np.int64), out=cu[nimg + 2:])
+        cu_d = torch.from_numpy(cu).to(dev, non_blocking=True)
+        cu_n, cu_m = cu_d[:nimg + 1], cu_d[nimg + 1:]
     max_n = max(pos_per_img) if nimg else 0
     max_m = max(pos_per_img_t) if nimg else 0
-    loss = torch.empty(nimg, dtype=torch.float32, device=dev)
-    slots = torch.empty(nimg, B, dtype=torch.float32, device=dev) if want_slots else None
-    valid = torch.empty(nimg, dtype=torch.int32, device=dev)
-    nits = torch.empty(nimg, dtype=torch.int32, device=dev)
-    grad_xs = torch.empty_like(xs)
-    grad_ws = torch.empty(xs.shape[:2], dtype=torch.float32, device=dev)
+    # outputs are views of two allocations (16-byte aligned segments) instead of six
+    r4 = lambda v: (v + 3) & ~3
+    n_gx, n_gw, n_l, n_s = xs.numel(), sum_n * B, nimg, (nimg * B if want_slots else 0)
+    fbuf = torch.empty(r4(n_gx) + r4(n_gw) + r4(n_l) + r4(n_s), dtype=torch.float32, device=dev)
+    ibuf = torch.empty(r4(nimg) * 2, dtype=torch.int32, device=dev)
+    o = 0
+    grad_xs = fbuf[o:o + n_gx].view(xs.shape); o += r4(n_gx)
+    grad_ws = fbuf[o:o + n_gw].view(xs.shape[:2]); o += r4(n_gw)
+    loss = fbuf[o:o + n_l]; o += r4(n_l)
+    slots = fbuf[o:o + n_s].view(nimg, B) if want_slots else None
+    valid, nits = ibuf[:nimg], ibuf[r4(nimg):r4(nimg) + nimg]
     if cfg.loss != "sinkhorn":
         kind = {"gaussian": 0, "laplacian": 1, "energy": 2}[cfg.loss]
         with torch.cuda.device(dev):
@@ -177,3 +186,73 @@ def normalize_in_place(xy: torch.Tensor, w: float, h: float) -> torch.Tensor:
     if xy.requires_grad:
         return _NormalizeInPlace.apply(xy, scale)
     return xy.div_(scale)
+
+
+class GatherDecodeFunction(torch.autograd.Function):
+    """``pred_reg`` levels -> decoded key-points of the positive cells, without flattening the head outputs
+    (``kdot_gather_decode_fwd`` / ``_bwd``).
+
+    ``apply(pos_inds, cls_label, anchors_pos, bbox_trans_pos, *pred_reg)`` returns ``(npos*8, 2)`` pixel key-points, the
+    tensor the reference builds at ``losses/kd_loss.py:47-50`` from ``pred_reg_flatten[pos_inds]``.  Backward writes
+    the 16 offset gradients of every positive cell straight into per-level gradients (views of ONE zero-filled
+    allocation)."""
+
+    @staticmethod
+    def forward(ctx, pos_inds, cls_label, anchors_pos, bbox_trans_pos, *pred_reg):
+        L = _lib.lib()
+        nlvl = len(pred_reg)
+        nimg, ch = pred_reg[0].shape[0], pred_reg[0].shape[1]
+        if ch % 16:
+            raise ValueError("pred_reg levels must have C*16 channels")
+        dev = pred_reg[0].device
+        levels = []
+        for r in pred_reg:
+            if r.dim() != 4 or r.shape[0] != nimg or r.shape[1] != ch:
+                raise ValueError("inconsistent pred_reg level shapes")
+            _check_f32_cuda("pred_reg level", r.detach() if r.is_contiguous() else r.detach().contiguous())
+            levels.append(r.detach() if r.is_contiguous() else r.detach().contiguous())
+        npos = int(pos_inds.shape[0])
+        pos_inds = pos_inds.to(torch.int64).contiguous()
+        cls_label = cls_label.to(torch.int64).contiguous()
+        _check_f32_cuda("anchors", anchors_pos, (npos, 4))
+        if bbox_trans_pos is not None:
+            bbox_trans_pos = bbox_trans_pos.to(torch.float32).contiguous()
+            _check_f32_cuda("bbox_trans", bbox_trans_pos, (npos, 2, 3))
+        xy = torch.empty(npos * 8, 2, dtype=torch.float32, device=dev)
+        hw = (C.c_int32 * nlvl)(*[int(r.shape[2] * r.shape[3]) for r in levels])
+        ptrs = (C.c_void_p * nlvl)(*[r.data_ptr() for r in levels])
+        with torch.cuda.device(dev):
+            rc = L.kdot_gather_decode_fwd(ptrs, hw, nlvl, nimg, ch // 16, pos_inds.data_ptr(), cls_label.data_ptr(),
+                                          anchors_pos.data_ptr(), _ptr(bbox_trans_pos), npos, xy.data_ptr(),
+                                          torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "kdot_gather_decode_fwd")
+        ctx.save_for_backward(pos_inds, cls_label, anchors_pos, bbox_trans_pos)
+        ctx.shapes = [tuple(r.shape) for r in levels]
+        ctx.hw, ctx.nimg, ctx.ncls = hw, nimg, ch // 16
+        return xy
+
+    @staticmethod
+    def backward(ctx, g_xy):
+        L = _lib.lib()
+        pos_inds, cls_label, anchors_pos, bbox_trans_pos = ctx.saved_tensors
+        dev = g_xy.device
+        npos = int(pos_inds.shape[0])
+        g_xy = g_xy.contiguous()
+        sizes = [int(np.prod(s)) for s in ctx.shapes]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)  # one memset for every level
+        grads, o = [], 0
+        for s, n in zip(ctx.shapes, sizes):
+            grads.append(flat[o:o + n].view(s))
+            o += n
+        ptrs = (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+        with torch.cuda.device(dev):
+            rc = L.kdot_gather_decode_bwd(g_xy.data_ptr(), ctx.hw, len(grads), ctx.nimg, ctx.ncls, pos_inds.data_ptr(),
+                                          cls_label.data_ptr(), anchors_pos.data_ptr(), _ptr(bbox_trans_pos), npos, ptrs,
+                                          torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "kdot_gather_decode_bwd")
+        return (None, None, None, None, *grads)
+
+
+def gather_decode(pred_reg, pos_inds, cls_label, anchors_pos, bbox_trans_pos=None):
+    """Decoded ``(npos*8, 2)`` pixel key-points of the positive cells, gathered from the per-level head outputs."""
+    return GatherDecodeFunction.apply(pos_inds, cls_label, anchors_pos.contiguous(), bbox_trans_pos, *pred_reg)

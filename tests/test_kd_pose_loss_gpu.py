@@ -53,7 +53,8 @@ def test_losses_and_gradients_match_reference():
     want = z["post_kp_2d"] / np.array([640.0, 480.0], np.float32)
     assert np.array_equal(pred_t["post_kp_2d"].cpu().numpy(), want.astype(np.float32))
 
-    g = torch.autograd.grad(kd_loss, pc + pr, allow_unused=True)
+    g = torch.autograd.grad(kd_loss, pc + pr, allow_unused=True, retain_graph=True)
+    g_all = torch.autograd.grad(cls_loss * 0.1 + reg_loss + 5.0 * kd_loss, pc + pr, allow_unused=True)
     for l in range(4):
         ref_c = _dense(z, "gkd_cls", l, s_cls[l].shape)
         ref_r = _dense(z, "gkd_reg", l, s_reg[l].shape)
@@ -68,4 +69,15 @@ def test_losses_and_gradients_match_reference():
             # d/d(offsets) inherits the fp32 noise of the REFERENCE's own d/dx (2e-4..6e-3 rel. at eps = 1e-6,
             # SURVEY.md fact 3): the OT-boundary tests arbitrate that tensor against the fp64 oracle.
             assert np.abs(got_r - ref_r).max() <= 1e-2 * np.abs(ref_r).max()
+    # the weighted total of the three losses, as train_kd.py combines them: focal-loss gradient on every class logit,
+    # regression + distillation gradient on the positive cells' offsets (through the fused gather/decode epilogue)
+    for l in range(4):
+        ref_r = _dense(z, "gall_reg", l, s_reg[l].shape)
+        got_r = np.zeros_like(ref_r) if g_all[4 + l] is None else g_all[4 + l].cpu().numpy()
+        assert np.array_equal(np.flatnonzero(got_r), np.flatnonzero(ref_r))
+        if np.abs(ref_r).max() > 0:
+            assert np.abs(got_r - ref_r).max() <= 1e-2 * np.abs(ref_r).max()
+        got_c = g_all[l].cpu().numpy().astype(np.float64)
+        assert abs(got_c.sum() - z["gall_cls_sum"][l]) <= 1e-4 * z["gall_cls_abs"][l]
+        assert abs(np.abs(got_c).sum() - z["gall_cls_abs"][l]) <= 1e-4 * z["gall_cls_abs"][l]
     assert loss_fn.step == 1 if hasattr(loss_fn, "step") else True
