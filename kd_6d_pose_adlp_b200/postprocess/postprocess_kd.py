@@ -15,6 +15,8 @@ budget ``nk``, per-level top-k, decode) for every (image, class) is ONE kernel l
 from __future__ import annotations
 
 import ctypes as C
+import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -65,27 +67,54 @@ def select_cells(box_cls, box_regression, anchor_sizes, anchor_strides, inferenc
     return out
 
 
-def _pnp_per_label(sel_np, i, targets_i, ncls, class_filter=None):
-    """Host part of ``pose_infer_ml`` (``postprocess_kd.py:158-203`` / ``postprocess.py:150-202``) for image ``i``:
-    for every candidate label (ascending), un-crop the selected key-points and run RANSAC-EPnP.
-    Yields ``(class_id, scores (n,), xy2d (n,8,2) float32 tensor, R, T)`` for every label whose PnP succeeded."""
-    import cv2
-
+def _prepare_pnp_tasks(sel_np, targets, ncls, class_filters=None):
+    """First half of the host part of ``pose_infer_ml`` (``postprocess_kd.py:158-189`` / ``postprocess.py:150-188``),
+    on the calling thread: for every image and candidate label (ascending), the selected key-points un-cropped to
+    full-image pixels -- ``inverse(A) @ (pt - t)`` for ALL rows of the mini-batch in one batched ``torch.inverse`` /
+    ``torch.bmm`` pair instead of one pair per (image, label).
+    Returns per image a list of ``(class_id, scores (n,), xy2d (n,8,2) float32 tensor, pts3d (n*8,3), K (3,3))``."""
     count, valid, score, kpts = sel_np["count"], sel_np["valid"], sel_np["score"], sel_np["kpts"]
-    K_np = targets_i.K.detach().cpu().numpy()
-    for c in range(ncls):
-        if valid[i, c].sum() == 0 or count[i, c] == 0:
-            continue
-        if class_filter is not None and c not in class_filter:
+    rows, owners = [], []
+    for i, c in np.argwhere((valid.sum(axis=-1) > 0) & (count > 0)).tolist():  # image-major, labels ascending
+        if class_filters is not None and c not in class_filters[i]:
             continue
         n = int(count[i, c])
-        xy2d = torch.from_numpy(kpts[i, c, :n].copy()).view(n, 2, 8).transpose(1, 2).contiguous()  # (n,8,2)
-        if targets_i.bbox_trans is not None:
-            bt = targets_i.bbox_trans.detach().cpu().to(torch.float32).view(1, 2, 3).repeat(n, 1, 1)
-            lin, off = bt[:, :, :2], bt[:, :, 2].unsqueeze(-1)
-            xy2d = torch.bmm(torch.inverse(lin), xy2d.transpose(1, 2).contiguous() - off).transpose(1, 2).contiguous()
-        xy3d_np = targets_i.keypoints_3d[c].detach().cpu().repeat(n, 1, 1).view(-1, 3).numpy()
-        ok, rot, trans, _inl = cv2.solvePnPRansac(xy3d_np, xy2d.view(-1, 2).numpy(), K_np, None,
+        owners.append((i, c, n))
+        rows.append(kpts[i, c, :n])
+    tasks = [[] for _ in targets]
+    if not owners:
+        return tasks
+    xy = torch.from_numpy(np.concatenate(rows, axis=0)).view(-1, 2, 8)  # (rows, 2, 8): x row, y row
+    with_bt = [targets[i].bbox_trans is not None for i, _c, _n in owners]
+    if any(with_bt):
+        eye = torch.tensor([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])
+        bt = torch.cat([(targets[i].bbox_trans.detach().cpu().to(torch.float32).view(1, 2, 3) if has else eye.view(1, 2, 3))
+                        .expand(n, 2, 3) for (i, _c, n), has in zip(owners, with_bt)], dim=0)
+        lin, off = bt[:, :, :2].contiguous(), bt[:, :, 2].unsqueeze(-1)
+        moved = torch.bmm(torch.inverse(lin), xy - off)
+        keep = torch.tensor(np.repeat(with_bt, [n for _i, _c, n in owners]))
+        xy = torch.where(keep.view(-1, 1, 1), moved, xy)
+    xy = xy.transpose(1, 2).contiguous()  # (rows, 8, 2)
+    k_np = {}
+    o = 0
+    for i, c, n in owners:
+        if i not in k_np:
+            k_np[i] = targets[i].K.detach().cpu().numpy()
+        pts3d = np.tile(targets[i].keypoints_3d[c].detach().cpu().numpy(), (n, 1))
+        tasks[i].append((c, score[i, c, :n].copy(), xy[o:o + n], pts3d, k_np[i]))
+        o += n
+    return tasks
+
+
+def _solve_image(tasks_i, first_only):
+    """Second half (``postprocess_kd.py:190-203``), safe to run on a worker thread (OpenCV releases the GIL):
+    RANSAC-EPnP per candidate label; ``first_only`` stops at the first label whose PnP succeeds
+    (``select_over_all_levels`` keeps only that one, ``postprocess_kd.py:71-97``)."""
+    import cv2
+
+    out = []
+    for c, sc, xy2d, pts3d, K_np in tasks_i:
+        ok, rot, trans, _inl = cv2.solvePnPRansac(pts3d, xy2d.view(-1, 2).numpy(), K_np, None,
                                                   flags=cv2.SOLVEPNP_EPNP, reprojectionError=5.0)
         if not ok:
             continue
@@ -93,7 +122,10 @@ def _pnp_per_label(sel_np, i, targets_i, ncls, class_filter=None):
         T = trans.reshape(-1, 1)
         if np.isnan(R.sum()) or np.isnan(T.sum()):
             continue
-        yield c, score[i, c, :n].copy(), xy2d, R, T
+        out.append((c, sc, xy2d, R, T))
+        if first_only:
+            break
+    return out
 
 
 class _SelectingPostProcessor(nn.Module):
@@ -108,6 +140,28 @@ class _SelectingPostProcessor(nn.Module):
         self.sym_types = sym_types
         self.symmetry_fn = symmetry_fn  # libs.utils.pose_symmetry_handling of the host repo (rotation only)
         self.last_selection = None
+        # per-image RANSAC-EPnP calls are independent and OpenCV releases the GIL: run them on a host thread pool
+        # (SURVEY.md section 8(f) item 2).  cv2's RANSAC seeds its own RNG per call, so results do not depend on
+        # the schedule.  `pnp_threads = 1` restores the reference's serial loop.
+        self.pnp_threads = min(16, len(os.sched_getaffinity(0))) if hasattr(os, "sched_getaffinity") else 4
+        self._pool = None
+
+    def _map_images(self, fn, nimg):
+        """``[fn(i) for i in range(nimg)]`` on the host thread pool (ordered)."""
+        if self.pnp_threads <= 1 or nimg <= 1:
+            return [fn(i) for i in range(nimg)]
+        import cv2
+
+        if self._pool is None or self._pool._max_workers != self.pnp_threads:
+            self._pool = ThreadPoolExecutor(max_workers=self.pnp_threads, thread_name_prefix="kdot-pnp")
+        # OpenCV serialises concurrent callers on its own (idle for PnP) worker pool: switch it off for the duration
+        # of the map (measured: 1.6 ms/image serial or pooled with it on, 0.42 ms/image on 8 host threads with it off)
+        inner = cv2.getNumThreads()
+        cv2.setNumThreads(1)
+        try:
+            return list(self._pool.map(fn, range(nimg)))
+        finally:
+            cv2.setNumThreads(inner)
 
     def _select(self, box_cls, box_regression):
         sel = select_cells(box_cls, box_regression, self.box_coder.anchor_sizes, self.box_coder.anchor_strides,
@@ -141,8 +195,10 @@ class PostProcessorKD(_SelectingPostProcessor):
         nimg, ncls = self._select(box_cls, box_regression)
         dev = box_cls[0].device
         results = [[], [], [], []]
+        tasks = _prepare_pnp_tasks(self.last_selection, targets, ncls)
+        solved = self._map_images(lambda i: _solve_image(tasks[i], first_only=True), nimg)
         for i in range(nimg):
-            picked = next(_pnp_per_label(self.last_selection, i, targets[i], ncls), None)
+            picked = solved[i][0] if solved[i] else None
             if picked is not None:
                 c, sc, xy2d, R, T = picked
                 n = len(sc)
@@ -165,14 +221,11 @@ class PostProcessor(_SelectingPostProcessor):
 
     def forward(self, box_cls, box_regression, targets, anchors=None):
         nimg, ncls = self._select(box_cls, box_regression)
-        results = []
-        for i in range(nimg):
-            present = set(int(v) for v in targets[i].class_ids.detach().cpu().reshape(-1).tolist())
-            per_img = []
-            for c, sc, xy2d, R, T in _pnp_per_label(self.last_selection, i, targets[i], ncls, class_filter=present):
-                per_img.append([float(sc.max()), int(c), self._symmetry(c, R), T, xy2d])
-            results.append(per_img)
-        return results
+        present = [set(int(v) for v in targets[i].class_ids.detach().cpu().reshape(-1).tolist()) for i in range(nimg)]
+        tasks = _prepare_pnp_tasks(self.last_selection, targets, ncls, class_filters=present)
+        solved = self._map_images(lambda i: _solve_image(tasks[i], first_only=False), nimg)
+        return [[[float(sc.max()), int(c), self._symmetry(c, R), T, xy2d] for c, sc, xy2d, R, T in per_img]
+                for per_img in solved]
 
 
 def teacher_knowledge(post_processor, pred_cls, pred_reg, targets, anchors=None):

@@ -92,3 +92,50 @@ def test_kd_pose_loss_class_factory_keeps_reference_signature():
                GnD=2, GLEVEL="point")
     obj = cls(2.0, 0.25, [32], [8], "SSC", 10, 1.0, 9, [1] * 9, [1.0], None, cfg)
     assert isinstance(obj.kd_loss, SamplesLoss) and obj.weighted_ot and not obj.wot_detach and not hasattr(obj, "step")
+
+
+def test_pnp_thread_pool_gives_the_serial_results():
+    """Host part of PostProcessorKD / PostProcessor (postprocess_kd.py:158-203): the per-image RANSAC-EPnP calls on
+    the thread pool return exactly what the reference's serial loop returns, in image order."""
+    pytest.importorskip("cv2")
+    from kd_6d_pose_adlp_b200.postprocess.postprocess_kd import _SelectingPostProcessor, _prepare_pnp_tasks, _solve_image
+    from tests import doubles, scenario
+
+    rng = np.random.default_rng(5)
+    nimg, ncls, cap, n = 12, 15, 16, 10
+    K = np.asarray(scenario.INTERNAL_K, np.float32).reshape(3, 3)
+    box = np.array([[sx, sy, sz] for sx in (-40, 40) for sy in (-35, 35) for sz in (-45, 45)], np.float32)
+    sel = dict(count=np.zeros((nimg, ncls), np.int32), valid=np.zeros((nimg, ncls, 5), np.int32),
+               score=np.zeros((nimg, ncls, cap), np.float32), kpts=np.zeros((nimg, ncls, cap, 16), np.float32))
+    targets = []
+    for i in range(nimg):
+        T = np.array([rng.normal(0, 60), rng.normal(0, 40), 900 + rng.normal(0, 50)], np.float32)
+        cam = box + T
+        uv = (K @ cam.T).T
+        uv = uv[:, :2] / uv[:, 2:3]
+        s, cx, cy = 1.6, float(uv[:, 0].mean()), float(uv[:, 1].mean())
+        bt = np.array([[s, 0, 128 - s * cx], [0, s, 128 - s * cy]], np.float32)
+        crop = uv @ bt[:, :2].T + bt[:, 2]
+        if i != 3:  # image 3 selects nothing
+            sel["count"][i, 0] = n
+            sel["valid"][i, 0, 1] = n
+            noisy = crop[None] + rng.normal(0, 0.7, (n, 8, 2)).astype(np.float32)
+            sel["kpts"][i, 0, :n] = np.concatenate([noisy[:, :, 0], noisy[:, :, 1]], axis=1)
+            sel["score"][i, 0, :n] = rng.uniform(0.4, 0.9, n)
+        targets.append(doubles.Target(torch.from_numpy(K), [torch.from_numpy(box)] * ncls, torch.from_numpy(bt)))
+
+    pp = _SelectingPostProcessor(0.1, None, 10, 1.0, None)
+    tasks = _prepare_pnp_tasks(sel, targets, ncls)
+    fn = lambda i: (_solve_image(tasks[i], first_only=True) or [None])[0]
+    pp.pnp_threads = 1
+    serial = pp._map_images(fn, nimg)
+    pp.pnp_threads = 6
+    pooled = pp._map_images(fn, nimg)
+    assert serial[3] is None and pooled[3] is None
+    assert sum(r is not None for r in serial) == nimg - 1
+    for a, b in zip(serial, pooled):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a[0] == b[0] and np.array_equal(a[1], b[1]) and torch.equal(a[2], b[2])
+            assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+            assert np.abs(a[4].reshape(-1)[2] - 900) < 120  # a sane pose, not a degenerate RANSAC result
