@@ -42,6 +42,9 @@ WORKLOADS = {
     "ape_b64": dict(nimg=64, dense=None, desc="LINEMOD-ape shape: B=8 keypoint slots, N~U{8..12} student / "
                     "M~U{8..12} teacher cells per image (5% empty teachers), D=2, batch 64 per GPU, "
                     "sinkhorn p=2 blur=1e-3 scaling=0.5 reach=0.5"),
+    # multi-object images (e.g. 5-12 objects x ~10 cells): the 33..256-point range of the CTA-resident tiled kernel
+    "multi_b64": dict(nimg=64, dense=None, n_range=(40, 120), m_range=(40, 120), desc="multi-object shape: N, M ~ U{40..120} "
+                      "cells per image (5% empty teachers), B=8, D=2, batch 64 per GPU"),
     # BASELINE.json configs[2] variant 3b: every cell of the darknet_tiny / darknet53 grids
     "dense_b32": dict(nimg=32, dense=(1360, 1364), desc="all cells: N=1360 student / M=1364 teacher cells per "
                       "image, B=8, D=2, batch 32 per GPU"),
@@ -67,8 +70,9 @@ def make_batch(workload, rank, nimg=None):
     from kd_6d_pose_adlp_b200.synthetic import ot_batch
 
     w = WORKLOADS[workload]
+    extra = {k: w[k] for k in ("n_range", "m_range") if k in w}
     return ot_batch(nimg or w["nimg"], seed=1234 + rank, dense=w["dense"], sigma=0.05 if w["dense"] is None else 0.1,
-                    B=w.get("B", 8), D=w.get("D", 2))
+                    B=w.get("B", 8), D=w.get("D", 2), **extra)
 
 
 def algorithmic_work(batch, nits):
@@ -355,8 +359,6 @@ def host_e2e(batch, dev_index, steps, warmup, barrier, cfg=CFG):
 def kernel_name(max_n, max_m, launches_per_step):
     if max_n + max_m <= 32:
         return "kdot_small_fast_kernel"
-    if max_n + max_m <= 64:
-        return "kdot_small_kernel"
     return "kdot_tiled_kernel" if launches_per_step == 2 else "kdot_stream_kernel"
 
 
@@ -364,7 +366,7 @@ def ncu_traffic_bytes(kernel, workload):
     """DRAM bytes (read + write) of one launch of `kernel` from the committed `ncu --set full` summary of the same
     workload (profiles/r01_prof_*_ncu_summary.txt), or None when no capture of that kernel ON THAT WORKLOAD is on file."""
     tag = {("kdot_small_fast_kernel", "ape_b64"): "small_fast", ("kdot_stream_kernel", "dense_b32"): "stream",
-           ("kdot_tiled_kernel", "dense_b32"): "tiled"}.get((kernel, workload))
+           ("kdot_tiled_kernel", "multi_b64"): "tiled"}.get((kernel, workload))
     path = os.path.join(ROOT, "profiles", f"r01_prof_{tag}_ncu_summary.txt")
     if tag is None or not os.path.exists(path):
         return None

@@ -37,16 +37,26 @@ void count_launches(unsigned n) { g_launches.fetch_add(n, std::memory_order_rela
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static size_t device_smem_limit_hint();
-static bool small_path(int max_n, int max_m, int B, int D = 2) { return D == 2 && max_n + max_m <= 64 && B <= 16; }
+// Kernel families (crossovers measured with tools/size_sweep.py on B200):
+//   SMALL   D = 2, p = 2, N + M <= 32 points per image, B <= 16: one warp per (image, slot), all in registers
+//   TILED   D = 2, p = 2, N + M <= kTiledMaxPoints: one CTA per (image, slot), cloud resident in shared memory,
+//           CTA barrier between rounds (1.2-2x faster than the streaming kernel for 33..256 points)
+//   STREAM  everything else (any size, D in {1,2,3,4,8,16}, p = 1): cooperative persistent kernel, chip-wide FIFO
+// KDOT_FORCE_PATH=tiled|stream overrides the size rule where the forced kernel applies (tuning / tests).
+enum KernelPath { PATH_SMALL = 0, PATH_TILED = 1, PATH_STREAM = 2 };
+constexpr int kTiledMaxPoints = 256;
 
-// 0 = tiled (one CTA per problem, cloud resident in shared memory), 1 = streaming cooperative kernel
-static int large_path(int max_n, int max_m, int D) {
-  // default: the streaming cooperative kernel (chip-wide dynamic balance, any size, any supported D);
-  // KDOT_FORCE_PATH=tiled selects the one-CTA-per-problem shared-memory kernel where it applies (D = 2, cloud fits)
+static bool small_path(int max_n, int max_m, int B, int D = 2) { return D == 2 && max_n + max_m <= 32 && B <= 16; }
+
+static KernelPath choose_path(int max_n, int max_m, int B, int D, float p) {
+  if (p != 2.0f) return PATH_STREAM;
   const char* env = getenv("KDOT_FORCE_PATH");
-  const bool fits = D == 2 && tiled_smem_bytes(max_n, max_m) <= device_smem_limit_hint();
-  if (env && env[0] == 't' && fits) return 0;
-  return 1;
+  const bool tiled_ok = D == 2 && tiled_smem_bytes(max_n, max_m) <= device_smem_limit_hint();
+  if (small_path(max_n, max_m, B, D)) return PATH_SMALL;
+  if (env && env[0] == 't' && tiled_ok) return PATH_TILED;
+  if (env && env[0] == 's') return PATH_STREAM;
+  if (tiled_ok && max_n + max_m <= kTiledMaxPoints) return PATH_TILED;
+  return PATH_STREAM;
 }
 
 struct WorkspacePlan {
@@ -92,9 +102,12 @@ size_t kdot_workspace_bytes_ex(int nimg, int max_n, int max_m, int B, int D, flo
 }
 
 size_t kdot_workspace_bytes(int nimg, int max_n, int max_m, int B, int D) {
-  if (nimg <= 0 || small_path(max_n, max_m, B, D)) return 0;
-  if (large_path(max_n, max_m, D) == 0) return plan_workspace(nimg, B).total;
-  return stream_supports_dim(D) ? stream_workspace_bytes(nimg, max_n, max_m, B, D) : 0;
+  if (nimg <= 0) return 0;
+  switch (choose_path(max_n, max_m, B, D, 2.0f)) {
+    case PATH_SMALL: return 0;
+    case PATH_TILED: return plan_workspace(nimg, B).total;
+    default: return stream_supports_dim(D) ? stream_workspace_bytes(nimg, max_n, max_m, B, D) : 0;
+  }
 }
 
 int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt, const int32_t* cu_n,
@@ -108,7 +121,7 @@ int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt
     return fail(KDOT_E_BADARG, "NULL required pointer");
   if (!stream_supports_dim(D)) return fail(KDOT_E_BADARG, "D must be one of 1, 2, 3, 4, 8, 16");
   if (normalize && D != 2) return fail(KDOT_E_BADARG, "normalize requires D == 2 (losses/loss_libs.py:7)");
-  if (normalize == 2 && !(p == 2.0f && small_path(max_n, max_m, B, D) && max_n + max_m <= 32))
+  if (normalize == 2 && !(choose_path(max_n, max_m, B, D, p) == PATH_SMALL))
     return fail(KDOT_E_BADARG, "normalize == 2 (no write-back) is only available on the small fused path");
   if (p != 2.0f && p != 1.0f) return fail(KDOT_E_BADARG, "p must be 1 or 2");
   if (p == 1.0f && D != 2) return fail(KDOT_E_BADARG, "p == 1 is implemented for D == 2 only");
@@ -143,16 +156,16 @@ int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt
   prm.dbg_clk = g_dbg_clk;
   cudaStream_t stream = (cudaStream_t)cuda_stream;
 
-  const bool p1 = p == 1.0f;  // cost |x - y|: served by the streaming kernel for every size
-  if (!p1 && small_path(max_n, max_m, B, D)) {
+  const KernelPath path = choose_path(max_n, max_m, B, D, p);  // p = 1 (cost |x - y|): streaming kernel, every size
+  if (path == PATH_SMALL) {
     cudaError_t e = launch_small(prm, max_n, max_m, stream);
-    if (e != cudaSuccess) return fail_cuda(e, "kdot_small_kernel");
+    if (e != cudaSuccess) return fail_cuda(e, "kdot_small_fast_kernel");
     count_launches(1);
     return KDOT_OK;
   }
   const size_t need = kdot_workspace_bytes_ex(nimg, max_n, max_m, B, D, p);
   if (!workspace || workspace_bytes < need) return fail(KDOT_E_WORKSPACE, "workspace too small (see kdot_workspace_bytes)");
-  if (p1 || large_path(max_n, max_m, D) == 1) {
+  if (path == PATH_STREAM) {
     cudaError_t e = launch_stream(prm, D, max_n, max_m, workspace, stream);
     if (e != cudaSuccess) return fail_cuda(e, "kdot_stream_kernel");
     count_launches(1);
@@ -338,7 +351,7 @@ int kdot_sinkhorn_fwd_bwd_host(kdot_host_ctx* c, float* xs_h, const float* ws_h,
   // transfer, small outputs written by the kernel straight into the mapped pinned staging area (posted PCIe writes;
   // removes the D2H copy-engine launch, ~8-10 us of fixed latency).  2: small problems also READ their inputs from the
   // mapped staging area (each element is read exactly once by the fused kernel), so the step is one kernel + one sync.
-  const bool small = p == 2.0f && small_path(max_n, max_m, B, D) && max_n + max_m <= 32;
+  const bool small = choose_path(max_n, max_m, B, D, p) == PATH_SMALL;
   const bool zc_out = c->zero_copy >= 1 && out_bytes <= (1u << 20) && !(normalize && write_back_normalized);
   const bool zc_in = c->zero_copy >= 2 && small && zc_out && in_bytes <= (1u << 20);
   char* in_base = zc_in ? c->pin_in_dev : c->dev_in;

@@ -63,6 +63,12 @@ struct SinkhornParams {
   long long* dbg_clk;     // optional [nimg][16] SM-clock stamps / counters (kdot_debug_set_clock_buffer), NULL in production
 };
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ void dbg_stamp(const SinkhornParams& p, int img, int k) {
   if (p.dbg_clk && threadIdx.x == 0) p.dbg_clk[(size_t)img * 16 + k] = clock64();
 }

@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
   const int nprob = b.nimg * B;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int strideP = p.strideP;
+  if (b.dbg_clk && blockIdx.x == 0 && threadIdx.x == 0) b.dbg_clk[0] = (long long)global_ns();
   extern __shared__ __align__(16) float s_tiles[];  // per warp: 2 x (D+1) x T floats (cp.async column tiles)
   float* wsm = s_tiles + (size_t)warp * stream_warp_smem_floats<D>();
   __shared__ float s_box[kStreamThreads / 32][2 * D];
@@ -433,6 +434,7 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nprob; q += gridDim.x * blockDim.x) p.done[q] = 0u;
   grid.sync();
 
+  if (b.dbg_clk && blockIdx.x == 0 && threadIdx.x == 0) b.dbg_clk[1] = (long long)global_ns();
   // ---------------- phase 0b: stage problems (SoA, padded) ----------------
   int max_rounds = 0;
   for (int i = 0; i < b.nimg; ++i) max_rounds = max(max_rounds, b.sched_rounds[i]);
@@ -472,6 +474,7 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
   }
   grid.sync();
 
+  if (b.dbg_clk && blockIdx.x == 0 && threadIdx.x == 0) b.dbg_clk[2] = (long long)global_ns();
   // ---------------- rounds: dataflow over a single global FIFO of warp units ----------------
   // Unit ids enumerate (round, problem, unit-in-problem) in that order.  A unit of round r may start once all units
   // of round r-1 of ITS problem have finished (done[prob] == r * upp); because ids are handed out in FIFO order and
@@ -489,6 +492,9 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
     const int r = (int)(id / (unsigned long long)upr);
     const long long u = (long long)(id - (unsigned long long)r * (unsigned long long)upr);
     const int prob = (int)(u / p.upp), uu = (int)(u - (long long)prob * p.upp);
+    // profiling aid (kdot_debug_set_clock_buffer): globaltimer stamps of problem 0's units, [8 + (r*upp+uu)*4 + k]
+    long long* stamp = (b.dbg_clk && prob == 0 && lane == 0 && r < 64) ? b.dbg_clk + 8 + ((size_t)r * p.upp + uu) * 4 : nullptr;
+    if (stamp) stamp[0] = (long long)global_ns();
     if (r > 0) {
       if (lane == 0) {
         const unsigned int need = (unsigned int)r * (unsigned int)p.upp;
@@ -501,12 +507,17 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
       }
       __syncwarp();
     }
+    if (stamp) stamp[1] = (long long)global_ns();
     stream_unit<D, R, P1>(p, r, prob, uu, lane, wsm);
+    if (stamp) stamp[2] = (long long)global_ns();
     __threadfence();
     __syncwarp();
     if (lane == 0) atomicAdd(p.done + prob, 1u);
+    if (stamp) stamp[3] = (long long)global_ns();
   }
+  if (b.dbg_clk && blockIdx.x == 0 && threadIdx.x == 0) b.dbg_clk[3] = (long long)global_ns();
   grid.sync();
+  if (b.dbg_clk && blockIdx.x == 0 && threadIdx.x == 0) b.dbg_clk[4] = (long long)global_ns();
 
   // ---------------- final: fixed-order loss reduction, one warp per image ----------------
   for (int img = blockIdx.x * nwarps + warp; img < b.nimg; img += gridDim.x * nwarps) {

@@ -19,11 +19,14 @@ namespace kdot {
 #ifndef KDOT_TILED_THREADS
 #define KDOT_TILED_THREADS 256
 #endif
+// tuning (tools/size_sweep.py on B200, 64 images): this kernel serves the 65..256-point range, where one row per lane
+// (32-row warp units: 16 units per round at N = M = 128 for the CTA's 8 warps) at 64 registers / 4 CTAs per SM beats
+// 2 and 4 rows per lane; above ~256 points the streaming kernel's chip-wide balance wins (kdot_api.cu: choose_path)
 #ifndef KDOT_TILED_ROWS
-#define KDOT_TILED_ROWS 4
+#define KDOT_TILED_ROWS 1
 #endif
 #ifndef KDOT_TILED_MINBLOCKS
-#define KDOT_TILED_MINBLOCKS 2
+#define KDOT_TILED_MINBLOCKS 4
 #endif
 constexpr int kTiledThreads = KDOT_TILED_THREADS;
 constexpr int kRows = KDOT_TILED_ROWS;       // rows per lane

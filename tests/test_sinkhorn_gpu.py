@@ -144,6 +144,15 @@ def test_large_path_kernels_match_oracle_d2(path, monkeypatch):
     check(ot_batch(4, seed=31, n_range=(33, 40), m_range=(33, 40)), reach=None, scaling=0.7)
 
 
+@pytest.mark.parametrize("n_range,m_range", [((16, 16), (16, 16)), ((16, 17), (16, 17)), ((3, 40), (2, 24)),
+                                             ((128, 128), (128, 128)), ((120, 129), (126, 128))])
+def test_default_dispatch_around_the_kernel_boundaries(n_range, m_range, monkeypatch):
+    """No path forced: 32 | 33 points (register kernel -> CTA-resident tiled kernel) and 256 | 257 points
+    (tiled -> streaming) give oracle-matching results on either side; the batch maximum decides for every image."""
+    monkeypatch.delenv("KDOT_FORCE_PATH", raising=False)
+    check(ot_batch(5, seed=sum(n_range) + 3 * sum(m_range), n_range=n_range, m_range=m_range, p_empty_teacher=0.2))
+
+
 def test_stream_kernel_clouds_beyond_shared_memory():
     """N = M = 3500 cells in one slot: too large for the tiled kernel's shared-memory plan -> streaming kernel."""
     from kd_6d_pose_adlp_b200.ops import OTConfig, ot_loss_batched

@@ -15,8 +15,10 @@ ncu --set full --clock-control none --import-source on -k regex:kdot_small_fast 
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-dense > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:kdot_stream -c 1 -o gpurun_out/${R}_prof_stream \
     python bench.py --workload dense_b32 --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-KDOT_FORCE_PATH=tiled ncu --set full --clock-control none --import-source on -k regex:kdot_tiled -c 1 -o gpurun_out/${R}_prof_tiled \
-    python bench.py --workload dense_b32 --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:kdot_tiled -s 3 -c 1 -o gpurun_out/${R}_prof_tiled \
+    python bench.py --workload multi_b64 --steps 2 --warmup 3 --no-cpu-baseline --no-dense > /dev/null 2>&1
+python bench.py --workload multi_b64 --steps 50 --warmup 5 --no-cpu-baseline --no-dense > gpurun_out/${R}_bench_multi_b64.json 2>> gpurun_out/${R}_bench.err
+python bench.py --workload zebra_b8 --steps 5 --warmup 3 --no-cpu-baseline --no-dense > gpurun_out/${R}_bench_zebra_b8.json 2>> gpurun_out/${R}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/${R}_launches_dense_b32.csv \
     python bench.py --workload dense_b32 --steps 3 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:kdot_select -c 1 -o gpurun_out/${R}_prof_select \

@@ -14,11 +14,9 @@ def run(b, cfg=OTConfig(), **kw):
     o = ot_loss_batched(t["xs"], t["ws"], t["xt"], t["wt"], b["pos_per_img"], b["pos_per_img_t"], cfg, **kw)
     torch.cuda.synchronize(); return float(o["loss_per_img"].sum())
 print("small fast", run(ot_batch(6, seed=1, p_empty_teacher=0.3)))
-print("small general", run(ot_batch(3, seed=2, n_range=(20, 30), m_range=(20, 30))))
-print("stream", run(ot_batch(3, seed=3, n_range=(40, 90), m_range=(40, 90), p_empty_teacher=0.3)))
-os.environ["KDOT_FORCE_PATH"] = "tiled"
-print("tiled", run(ot_batch(2, seed=4, n_range=(40, 90), m_range=(40, 90))))
-os.environ.pop("KDOT_FORCE_PATH")
+print("tiled (33..256 points)", run(ot_batch(3, seed=2, n_range=(20, 30), m_range=(20, 30))))
+print("stream", run(ot_batch(3, seed=3, n_range=(140, 190), m_range=(140, 190), p_empty_teacher=0.3)))
+print("tiled, empty teachers", run(ot_batch(4, seed=4, n_range=(40, 90), m_range=(40, 90), p_empty_teacher=0.5)))
 print("mmd", run(ot_batch(3, seed=5), OTConfig(loss="energy", blur=0.05)))
 print("p1", run(ot_batch(2, seed=6), OTConfig(p=1.0, blur=0.01)))
 x = torch.sigmoid(torch.randn(1, 60, 16)).to(dev); y = torch.sigmoid(torch.randn(1, 50, 16)).to(dev)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Kernel time / achieved FP32 throughput over problem sizes (N = M cells per image, B = 8, D = 2) on the GPU box:
-shows where each kernel family (small-fast <= 32 points, small 33..64, streaming above) sits against the roofline.
+shows where each kernel family (small-fast <= 32 points, CTA-resident tiled 33..256, streaming above) sits against the roofline.
 
     python tools/size_sweep.py [nimg] [n1,n2,...]
 """
