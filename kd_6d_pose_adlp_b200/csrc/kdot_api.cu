@@ -60,7 +60,7 @@ static KernelPath choose_path(int max_n, int max_m, int B, int D, float p) {
 }
 
 struct WorkspacePlan {
-  size_t off_sched, off_rounds, off_slot, off_ctr, total;
+  size_t off_sched, off_rounds, off_slot, off_ctr, off_order, total;
 };
 static WorkspacePlan plan_workspace(int nimg, int B) {
   WorkspacePlan w;
@@ -69,6 +69,7 @@ static WorkspacePlan plan_workspace(int nimg, int B) {
   w.off_rounds = o; o = align_up(o + (size_t)nimg * sizeof(int32_t), 256);
   w.off_slot = o;   o = align_up(o + (size_t)nimg * B * sizeof(float), 256);
   w.off_ctr = o;    o = align_up(o + (size_t)nimg * sizeof(unsigned int), 256);
+  w.off_order = o;  o = align_up(o + (size_t)nimg * sizeof(int32_t), 256);
   w.total = o;
   return w;
 }
@@ -177,6 +178,7 @@ int kdot_sinkhorn_fwd_bwd(float* xs, const float* ws, float* xt, const float* wt
   prm.sched_rounds = (int32_t*)(base + wp.off_rounds);
   prm.slot_loss = (float*)(base + wp.off_slot);
   prm.done_ctr = (unsigned int*)(base + wp.off_ctr);
+  prm.order = (int32_t*)(base + wp.off_order);
   bool too_large = false;
   cudaError_t e = launch_tiled(prm, max_n, max_m, stream, device_smem_limit(), &too_large);
   if (too_large) return fail(KDOT_E_TOOLARGE, "cloud does not fit the tiled kernel's shared-memory plan");

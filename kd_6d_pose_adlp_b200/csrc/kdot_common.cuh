@@ -60,6 +60,7 @@ struct SinkhornParams {
   int32_t* sched_rounds; // [nimg] number of rounds (nits + 2) or <0 status
   float* slot_loss;      // [nimg][B]
   unsigned int* done_ctr; // [nimg]
+  int32_t* order;         // [nimg] tiled path: images by descending size (rank -> image), written by the prep kernel
   long long* dbg_clk;     // optional [nimg][16] SM-clock stamps / counters (kdot_debug_set_clock_buffer), NULL in production
 };
 

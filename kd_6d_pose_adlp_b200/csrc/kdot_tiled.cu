@@ -68,6 +68,25 @@ __global__ void __launch_bounds__(256) kdot_prep_kernel(SinkhornParams prm) {
     minx = fminf(minx, v.x); maxx = fmaxf(maxx, v.x);
     miny = fminf(miny, v.y); maxy = fmaxf(maxy, v.y);
   }
+  // Rank of this image by pair count, descending (ties: lower index first).  The main kernel maps CTA k to the image
+  // of rank k / B: the hardware hands consecutive CTAs to different SMs, so every SM receives one problem from each
+  // size quantile and the single wave of resident CTAs is balanced even when cloud sizes vary several-fold.
+  {
+    const long long mine = (long long)(N + M) * (N + M);
+    int ahead = 0;
+    for (int j = threadIdx.x; j < prm.nimg; j += blockDim.x) {
+      const long long pj = (long long)(prm.cu_n[j + 1] - prm.cu_n[j]) + (long long)(prm.cu_m[j + 1] - prm.cu_m[j]);
+      const long long other = pj * pj;
+      ahead += (other > mine || (other == mine && j < img)) ? 1 : 0;
+    }
+    __shared__ int s_rank;
+    if (threadIdx.x == 0) s_rank = 0;
+    __syncthreads();
+    ahead = __reduce_add_sync(0xffffffffu, ahead);
+    if ((threadIdx.x & 31) == 0 && ahead) atomicAdd(&s_rank, ahead);
+    __syncthreads();
+    if (threadIdx.x == 0) prm.order[s_rank] = img;
+  }
   const bool skipped = (N == 0 || M == 0);
   minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -226,7 +245,8 @@ __device__ __forceinline__ void rows_reset(RowState<kGrad> (&st)[kRows]) {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tiled_kernel(SinkhornParams prm) {
   const int B = prm.B;
-  const int img = blockIdx.x / B, slot = blockIdx.x - img * B;
+  const int rank = blockIdx.x / B, slot = blockIdx.x - rank * B;
+  const int img = prm.order[rank];  // largest images first (see the prep kernel)
   const int nrounds = prm.sched_rounds[img];
   if (nrounds <= 0) return;  // skipped / degenerate image: prep kernel wrote the outputs
   const int nits = nrounds - 2;
