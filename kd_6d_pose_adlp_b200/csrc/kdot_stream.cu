@@ -37,7 +37,7 @@ namespace kdot {
 #define KDOT_STREAM_R2 2
 #endif
 constexpr int kStreamThreads = KDOT_STREAM_THREADS;
-constexpr float kTauS = 24.f;
+constexpr float kTauS = 80.f;  // re-base when a chunk sum exceeds 2^80 of the reference: rare, and fp32 keeps full precision below 2^127
 
 struct StreamParams {
   SinkhornParams b;
@@ -51,6 +51,11 @@ struct StreamParams {
   float* pot;    // [nprob][2][strideP]          S, C
   float* h;      // [nprob][2 buffers][2][strideP]
   float* term;   // [nprob][strideP]             weight * loss term of every row (final round)
+  int* perm;     // [nprob][strideP]             staged position -> cell index inside its cloud (-1 for pads)
+  float4* tbox;  // [nprob][strideP/32]          bounding box (min x, min y, max x, max y) of every 32-point tile (D = 2)
+  float* hmax;   // [nprob][2 buffers][2][strideP/32]  max of h over the tile, maintained by the units that write h
+  int* jb;       // [nprob][2][strideP]          per row and column set (own, cross): first column of the chunk that held
+                 //                              the row's running max in the previous round (seeds the next sweep)
   unsigned int* ctr;  // [KDOT_MAX_ROUNDS]       first 8 bytes: 64-bit head of the global unit FIFO
   unsigned int* done; // [nprob]                 finished units per problem (all rounds)
 };
@@ -62,6 +67,11 @@ struct URow {
   float2 mu;            // mref / (-coef), duplicated: folded into the squared-distance FMA chain
   float2 s;
   float2 g[GRAD ? D : 1];
+  // cold rounds (SKIP): the 32-column sub-tile that added the most to the running sum so far.  Its maximum is within a
+  // factor 32 (5 log2 units) of the row maximum, so it seeds the next round's sweep (urow_seed) with a reference that
+  // needs no re-basing and puts every far tile below the skip threshold from the first column on.
+  int jb;
+  float gbest, s0;
 };
 
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -143,6 +153,8 @@ __device__ __forceinline__ void stream_chunk(URow<D, R, GRAD> (&st)[R], const fl
         for (int d = 0; d < D; ++d) { st[k].g[d].x *= sc; st[k].g[d].y *= sc; }
       }
       st[k].mref = vm;
+      st[k].gbest *= sc;   // the sub-tile bookkeeping of stream_rows lives on the same scale as the sums
+      st[k].s0 *= sc;
       const float mu = vm * inv_ncoef;
       st[k].mu = make_float2(mu, mu);
       const float2 p0 = make_float2(ex2_approx(v0.x - vm), ex2_approx(v0.y - vm));
@@ -182,9 +194,23 @@ __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_g
 
 // R rows of this lane against columns [0, ncols) of one column set (ncols multiple of 4; SoA global arrays
 // pts[d][strideP], ch[]).  The h arrays are rewritten every round by other SMs: cp.async.cg reads them from L2.
-template <int D, int R, bool GRAD, bool FOLD, bool P1>
+// Tile-level skip data of one column set: bounding boxes and h maxima of its 32-column tiles.  For row i and a tile,
+//   hmax_tile + coef * dist^2(p_i, tile box)       (coef < 0)
+// bounds every soft-min argument of the row against the tile's columns from above; when it lies more than 140 below the
+// row's reference exponent for EVERY row of the warp, each ex2 of the tile would flush to exactly +0 in every lane
+// (128 = ex2.approx.ftz flush point, 12 more for the fp32 rounding of the bound), so the tile is skipped without
+// evaluating a single pair.  The result is bit-identical to evaluating it.
+struct TileSkip {
+  const float4* tbox;  // first tile of the column set: (min x, min y, max x, max y)
+  const float* hmax;   // same tiles, current h buffer
+};
+
+// SKIP: cold rounds of D = 2 problems staged in Morton order -- tile-level exact skipping (TileSkip) plus the sub-tile
+// bookkeeping that seeds the next round.
+template <int D, int R, bool GRAD, bool FOLD, bool P1, bool SKIP>
 __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const float* __restrict__ pts, int strideP,
-                                            const float* ch, int ncols, float coef, float* wsm, int lane) {
+                                            const float* ch, int ncols, float coef, float* wsm, int lane,
+                                            const TileSkip ts = TileSkip{}) {
   constexpr int T = stream_tile_cols<D>();
   const float2 coef2 = make_float2(coef, coef);
   const float inv_ncoef = -1.0f / coef;
@@ -207,13 +233,47 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
     __syncwarp();
     const float* tb = wsm + (t & 1) * (D + 1) * T;
     const int n = min(T, ncols - t * T);
-#pragma unroll 1
-    for (int j = 0; j < n; j += 4) {
-      float4 X[D];
+    unsigned int dead = 0u;  // bit s: 32-column sub-tile s of this tile contributes exactly nothing to any row of the warp
+    if (SKIP && D == 2) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) X[d] = *reinterpret_cast<const float4*>(tb + d * T + j);
-      const float4 H = *reinterpret_cast<const float4*>(tb + D * T + j);
-      stream_chunk<D, R, GRAD, FOLD, P1>(st, X, H, coef2, inv_ncoef, big);
+      for (int sb = 0; sb < T / 32; ++sb) {
+        if (sb * 32 >= n) break;
+        const float4 bx = ts.tbox[t * (T / 32) + sb];          // warp-uniform loads
+        const float hm = __ldcg(ts.hmax + t * (T / 32) + sb);
+        bool far = true;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const float px = -st[k].nx[0], py = -st[k].nx[D - 1];
+          const float dx = fmaxf(fmaxf(bx.x - px, px - bx.z), 0.f);
+          const float dy = fmaxf(fmaxf(bx.y - py, py - bx.w), 0.f);
+          far = far && (fmaf(coef, fmaf(dx, dx, dy * dy), hm) - st[k].mref < -140.f);
+        }
+        if (__all_sync(0xffffffffu, far)) dead |= 1u << sb;
+      }
+    }
+#pragma unroll 1
+    for (int sb = 0; sb < n; sb += 32) {
+      if (SKIP && D == 2 && ((dead >> (sb >> 5)) & 1u)) continue;
+      if (SKIP) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) st[k].s0 = st[k].s.x + st[k].s.y;
+      }
+      const int je = min(sb + 32, n);
+#pragma unroll 1
+      for (int j = sb; j < je; j += 4) {
+        float4 X[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) X[d] = *reinterpret_cast<const float4*>(tb + d * T + j);
+        const float4 H = *reinterpret_cast<const float4*>(tb + D * T + j);
+        stream_chunk<D, R, GRAD, FOLD, P1>(st, X, H, coef2, inv_ncoef, big);
+      }
+      if (SKIP) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const float gain = (st[k].s.x + st[k].s.y) - st[k].s0;
+          if (gain > st[k].gbest) { st[k].gbest = gain; st[k].jb = t * T + sb; }
+        }
+      }
     }
     __syncwarp();  // every lane is done with this buffer before tile t+2 overwrites it
   }
@@ -224,10 +284,47 @@ __device__ __forceinline__ void urow_reset(URow<D, R, GRAD> (&st)[R], float inv_
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     st[k].mref = kNegBig;
+    st[k].jb = 0;
+    st[k].gbest = 0.f;
+    st[k].s0 = 0.f;
     st[k].mu = make_float2(kNegBig * inv_ncoef, kNegBig * inv_ncoef);
     st[k].s = make_float2(0.f, 0.f);
 #pragma unroll
     for (int d = 0; d < (GRAD ? D : 1); ++d) st[k].g[d] = make_float2(0.f, 0.f);
+  }
+}
+
+// Cold rounds: start the sweep of row k with the reference exponent set to the max of the 4-column chunk that held
+// the row's running max in the PREVIOUS round (jb[k]).  It is a true value of this row, hence a valid lower bound of the
+// row max, and it is almost always within a few units of it: the far chunks of the (Morton-ordered) sweep are then
+// below the skip threshold from the first column on, and the climb towards the near region needs no re-basing.
+template <int D, int R, bool GRAD, bool P1>
+__device__ __forceinline__ void urow_seed(URow<D, R, GRAD> (&st)[R], const float* __restrict__ pts, int strideP,
+                                          const float* ch, float coef, const int (&jb)[R]) {
+  const float2 coef2 = make_float2(coef, coef);
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    float vm = kNegBig;
+#pragma unroll 2
+    for (int c = 0; c < 32; c += 4) {  // the clouds are padded to 32-point tiles: the whole sub-tile is readable
+      float2 q0 = make_float2(0.f, 0.f), q1 = q0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float4 X = *reinterpret_cast<const float4*>(pts + (size_t)d * strideP + jb[k] + c);
+        const float2 nd = make_float2(st[k].nx[d], st[k].nx[d]);
+        const float2 a0 = __fadd2_rn(make_float2(X.x, X.y), nd);
+        const float2 a1 = __fadd2_rn(make_float2(X.z, X.w), nd);
+        q0 = d == 0 ? __fmul2_rn(a0, a0) : __ffma2_rn(a0, a0, q0);
+        q1 = d == 0 ? __fmul2_rn(a1, a1) : __ffma2_rn(a1, a1, q1);
+      }
+      if (P1) { q0 = p1_norm(q0); q1 = p1_norm(q1); }
+      const float4 H = ld_cg4(ch + jb[k] + c);
+      const float2 v0 = __ffma2_rn(q0, coef2, make_float2(H.x, H.y));
+      const float2 v1 = __ffma2_rn(q1, coef2, make_float2(H.z, H.w));
+      vm = fmaxf(vm, fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y)));
+    }
+    st[k].mref = vm;
+    st[k].jb = jb[k];
   }
 }
 
@@ -239,6 +336,7 @@ __device__ __forceinline__ long long cell_index(const SinkhornParams& b, bool st
 // One warp unit: rows [blk*32R, blk*32R + 32R) of one cloud of problem `prob` against one column set, round r.
 template <int D, int R, bool P1>
 __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int prob, int uu, int lane, float* wsm) {
+  constexpr bool kSkip = (D == 2) && !P1;  // exact skipping of all-underflow chunks in the cold rounds (see stream_chunk)
   const SinkhornParams& b = p.b;
   const int B = b.B, strideP = p.strideP;
   const int img = prob / B, slot = prob - img * B;
@@ -265,6 +363,14 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   const float* hCc = hSc + strideP;
   float* hSn = p.h + ((size_t)prob * 4 + (cur ^ 1) * 2) * strideP;
   float* hCn = hSn + strideP;
+  int* jbS = p.jb + (size_t)prob * 2 * strideP;  // indexed by staged row position, like the potentials
+  int* jbC = jbS + strideP;
+  const int ntile = strideP >> 5;
+  const float4* tbox = p.tbox + (size_t)prob * ntile;
+  const float* hmSc = p.hmax + ((size_t)prob * 4 + cur * 2) * ntile;  // same layout as h, one value per 32 points
+  const float* hmCc = hmSc + ntile;
+  float* hmSn = p.hmax + ((size_t)prob * 4 + (cur ^ 1) * 2) * ntile;
+  float* hmCn = hmSn + ntile;
 
   if (last && rows_x) {
     if (!own) return;  // the student's last round is done by the "own" unit for both column sets
@@ -277,21 +383,32 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
       urow_reset<D, 1, true>(st, -1.0f / rc.coef);
 #pragma unroll
       for (int d = 0; d < D; ++d) st[0].nx[d] = -pts[(size_t)d * strideP + src];
-      stream_rows<D, 1, true, false, P1>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane);
+      TileSkip ts{};
+      if (kSkip) {
+        const int jb1[1] = {__ldcg(jbS + src)};
+        urow_seed<D, 1, true, P1>(st, pts, strideP, hSc, rc.coef, jb1);
+        ts.tbox = tbox; ts.hmax = hmSc;
+      }
+      stream_rows<D, 1, true, false, P1, kSkip>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane, ts);
       const float sS = st[0].s.x + st[0].s.y;
       const float S = rc.scale * (st[0].mref + lg2_approx(sS));
       float gS[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) gS[d] = (st[0].g[d].x + st[0].g[d].y) / sS;
       urow_reset<D, 1, true>(st, -1.0f / rc.coef);
-      stream_rows<D, 1, true, false, P1>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane);
+      if (kSkip) {
+        const int jb1[1] = {__ldcg(jbC + src)};
+        urow_seed<D, 1, true, P1>(st, pts + p.nqMax, strideP, hCc + p.nqMax, rc.coef, jb1);
+        ts.tbox = tbox + (p.nqMax >> 5); ts.hmax = hmCc + (p.nqMax >> 5);
+      }
+      stream_rows<D, 1, true, false, P1, kSkip>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane, ts);
       if (!act) continue;
       const float sC = st[0].s.x + st[0].s.y;
       const float C = rc.scale * (st[0].mref + lg2_approx(sC));
       const RowFinal f = row_final(S, C, rho, rc.eps);
       const float lam = rho < 0.0 ? 1.f : (float)(1.0 / (1.0 + (double)rc.eps / rho));
       const float gfac = rho < 0.0 ? 1.f : (float)((rho + 0.5 * (double)rc.eps) / rho) * lam;
-      const long long g = cell_index(b, true, b.cu_n[img] + i, slot);
+      const long long g = cell_index(b, true, b.cu_n[img] + p.perm[(size_t)prob * strideP + i], slot);
       const float wg = b.ws ? b.ws[g] : __fdiv_rn(1.0f, (float)N);
       p.term[(size_t)prob * strideP + i] = wg * f.term;
 #pragma unroll
@@ -322,11 +439,40 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   }
   // warm rounds (eps >= eps_0 / 256): reference exponent folded into the distance chain (one op less per pair)
   const float eps0 = b.sched[(size_t)img * KDOT_MAX_ROUNDS].eps;
-  if (!P1 && rc.eps * 256.0f >= eps0) stream_rows<D, R, false, !P1, false>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane);
-  else stream_rows<D, R, false, false, P1>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane);
+  int* jbArr = own ? jbS : jbC;
+  if (!P1 && rc.eps * 256.0f >= eps0) {
+    stream_rows<D, R, false, !P1, false, false>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane);
+  } else {
+    TileSkip ts{};
+    if (kSkip) {
+      int jbv[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) jbv[k] = __ldcg(jbArr + (ridx[k] >= 0 ? ridx[k] : rbase));
+      urow_seed<D, R, false, P1>(st, cpts, strideP, ch, rc.coef, jbv);
+      ts.tbox = tbox + ((cols_x ? 0 : p.nqMax) >> 5);
+      ts.hmax = (own ? hmSc : hmCc) + ((cols_x ? 0 : p.nqMax) >> 5);
+    }
+    stream_rows<D, R, false, false, P1, kSkip>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane, ts);
+  }
+  if (kSkip && !last) {  // per-tile maximum of the h values this unit is about to publish (rows of pass k = one tile)
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      float hv = kNegBig;
+      if (ridx[k] >= 0) {
+        const float lse = st[k].mref + lg2_approx(st[k].s.x + st[k].s.y);
+        const float nv = rc.scale * lse;
+        const float pv = r == 0 ? nv : 0.5f * (__ldcg((own ? potS : potC) + ridx[k]) + nv);
+        hv = fmaf(pv, rc.hmul, __ldcg(lw2 + ridx[k]));
+      }
+      hv = warp_max(hv);
+      const int tile = (rbase + blk * 32 * R + 32 * k) >> 5;
+      if (lane == 0 && tile < ntile && blk * 32 * R + 32 * k < rcount) (own ? hmSn : hmCn)[tile] = hv;
+    }
+  }
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     if (ridx[k] < 0) continue;
+    if (kSkip) jbArr[ridx[k]] = st[k].jb;
     const float lse = st[k].mref + lg2_approx(st[k].s.x + st[k].s.y);
     float* pot = own ? potS : potC;
     const float nv = rc.scale * lse;
@@ -438,38 +584,109 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
   // ---------------- phase 0b: stage problems (SoA, padded) ----------------
   int max_rounds = 0;
   for (int i = 0; i < b.nimg; ++i) max_rounds = max(max_rounds, b.sched_rounds[i]);
+  // One CTA per (problem, cloud).  D = 2 clouds of up to kSortMax points are staged in MORTON ORDER of their own
+  // bounding box (rank by counting over 32-bit keys <morton16 | index>: deterministic, O(n^2 / 256) per thread, a few
+  // microseconds): rows of a warp unit and columns of a chunk are then spatial neighbours, which is what lets the cold
+  // rounds skip whole chunks exactly (stream_chunk SKIP).  perm[] maps a staged position back to its cell.
   {
-    const long long total = (long long)nprob * strideP;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-      const int prob = (int)(t / strideP), q = (int)(t - (long long)prob * strideP);
+    constexpr int kSortMax = 4096;
+    unsigned int* keys = reinterpret_cast<unsigned int*>(s_tiles);
+    __shared__ float s_mm[kStreamThreads / 32][4];
+    for (int pc = blockIdx.x; pc < 2 * nprob; pc += gridDim.x) {
+      const int prob = pc >> 1;
+      const bool in_x = (pc & 1) == 0;
       const int img = prob / B, slot = prob - img * B;
-      if (b.sched_rounds[img] <= 0) continue;
+      if (b.sched_rounds[img] <= 0) continue;  // uniform per CTA
       const int n0 = b.cu_n[img], N = b.cu_n[img + 1] - n0;
       const int m0 = b.cu_m[img], M = b.cu_m[img + 1] - m0;
-      const bool in_x = q < p.nqMax;
-      const int i = in_x ? q : q - p.nqMax;
-      const bool real = in_x ? (i < N) : (i < M);
-      float l2 = kNegBig;
-      float v[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) v[d] = 0.f;
-      if (real) {
-        const long long g = cell_index(b, in_x, in_x ? n0 + i : m0 + i, slot);
-        const float* base = in_x ? b.xs : b.xt;
-        const float* wb = in_x ? b.ws : b.wt;
-#pragma unroll
-        for (int d = 0; d < D; ++d) v[d] = base[(size_t)D * g + d];
-        const float wg = wb ? wb[g] : __fdiv_rn(1.0f, (float)(in_x ? N : M));
-        l2 = (wg > 0.f ? logf(wg) : kLogZeroWeight) * kLog2e;
+      const int n = in_x ? N : M;
+      const int q0 = in_x ? 0 : p.nqMax;
+      const int cap = in_x ? p.nqMax : strideP - p.nqMax;
+      const float* base = in_x ? b.xs : b.xt;
+      const float* wb = in_x ? b.ws : b.wt;
+      const int c0 = in_x ? n0 : m0;
+      const bool sorted = D == 2 && n > 32 && n <= kSortMax;
+      if (sorted) {
+        float mnx = 3.0e38f, mny = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          const long long g = cell_index(b, in_x, c0 + i, slot);
+          const float vx = base[(size_t)D * g], vy = base[(size_t)D * g + D - 1];
+          mnx = fminf(mnx, vx); mxx = fmaxf(mxx, vx); mny = fminf(mny, vy); mxy = fmaxf(mxy, vy);
+        }
+        mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+        if (lane == 0) { s_mm[warp][0] = mnx; s_mm[warp][1] = mny; s_mm[warp][2] = mxx; s_mm[warp][3] = mxy; }
+        __syncthreads();
+        for (int wi = 0; wi < nwarps; ++wi) {
+          mnx = fminf(mnx, s_mm[wi][0]); mny = fminf(mny, s_mm[wi][1]);
+          mxx = fmaxf(mxx, s_mm[wi][2]); mxy = fmaxf(mxy, s_mm[wi][3]);
+        }
+        const float sx = mxx > mnx ? 255.0f / (mxx - mnx) : 0.f, sy = mxy > mny ? 255.0f / (mxy - mny) : 0.f;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          const long long g = cell_index(b, in_x, c0 + i, slot);
+          unsigned int qx = (unsigned int)fminf(fmaxf((base[(size_t)D * g] - mnx) * sx, 0.f), 255.f);
+          unsigned int qy = (unsigned int)fminf(fmaxf((base[(size_t)D * g + D - 1] - mny) * sy, 0.f), 255.f);
+          qx = (qx | (qx << 4)) & 0x0F0Fu; qx = (qx | (qx << 2)) & 0x3333u; qx = (qx | (qx << 1)) & 0x5555u;
+          qy = (qy | (qy << 4)) & 0x0F0Fu; qy = (qy | (qy << 2)) & 0x3333u; qy = (qy | (qy << 1)) & 0x5555u;
+          keys[i] = ((qx | (qy << 1)) << 16) | (unsigned int)i;  // unique: ties broken by the cell index
+        }
+        for (int i = n + threadIdx.x; i < ((n + 3) & ~3); i += blockDim.x) keys[i] = 0xffffffffu;
+        __syncthreads();
       }
+      for (int i = threadIdx.x; i < cap; i += blockDim.x) {
+        const bool real = i < n;
+        int rank = i;
+        if (sorted && real) {
+          const unsigned int ki = keys[i];
+          int c = 0;
+          for (int j = 0; j < n; j += 4) {
+            const uint4 kj = *reinterpret_cast<const uint4*>(keys + j);
+            c += (kj.x < ki) + (kj.y < ki) + (kj.z < ki) + (kj.w < ki);
+          }
+          rank = c;
+        }
+        const int q = q0 + rank;
+        float l2 = kNegBig;
+        float v[D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) p.pts[((size_t)prob * D + d) * strideP + q] = v[d];
-      p.lw2[(size_t)prob * strideP + q] = l2;
-      float* hb = p.h + (size_t)prob * 4 * strideP;
-      hb[q] = l2; hb[strideP + q] = l2; hb[2 * strideP + q] = l2; hb[3 * strideP + q] = l2;
-      p.pot[(size_t)prob * 2 * strideP + q] = 0.f;
-      p.pot[(size_t)prob * 2 * strideP + strideP + q] = 0.f;
-      p.term[(size_t)prob * strideP + q] = 0.f;
+        for (int d = 0; d < D; ++d) v[d] = 0.f;
+        if (real) {
+          const long long g = cell_index(b, in_x, c0 + i, slot);
+#pragma unroll
+          for (int d = 0; d < D; ++d) v[d] = base[(size_t)D * g + d];
+          const float wg = wb ? wb[g] : __fdiv_rn(1.0f, (float)n);
+          l2 = (wg > 0.f ? logf(wg) : kLogZeroWeight) * kLog2e;
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) p.pts[((size_t)prob * D + d) * strideP + q] = v[d];
+        p.lw2[(size_t)prob * strideP + q] = l2;
+        float* hb = p.h + (size_t)prob * 4 * strideP;
+        hb[q] = l2; hb[strideP + q] = l2; hb[2 * strideP + q] = l2; hb[3 * strideP + q] = l2;
+        p.pot[(size_t)prob * 2 * strideP + q] = 0.f;
+        p.pot[(size_t)prob * 2 * strideP + strideP + q] = 0.f;
+        p.term[(size_t)prob * strideP + q] = 0.f;
+        p.perm[(size_t)prob * strideP + q] = real ? i : -1;
+        p.jb[(size_t)prob * 2 * strideP + q] = 0;
+        p.jb[(size_t)prob * 2 * strideP + strideP + q] = 0;
+      }
+      __syncthreads();  // staged values of this cloud are visible to the whole CTA; keys may be reused
+      if (D == 2) {  // per 32-point tile: bounding box of its real points and the maximum of the initial h (= log weight)
+        const int ntile = strideP >> 5;
+        for (int tile = warp; tile * 32 < cap; tile += nwarps) {
+          const int q = q0 + tile * 32 + lane;
+          const bool real = tile * 32 + lane < cap && p.perm[(size_t)prob * strideP + q] >= 0;
+          const float vx = real ? p.pts[((size_t)prob * D) * strideP + q] : 0.f;
+          const float vy = real ? p.pts[((size_t)prob * D + D - 1) * strideP + q] : 0.f;
+          const float lo_x = warp_min(real ? vx : 3.0e38f), lo_y = warp_min(real ? vy : 3.0e38f);
+          const float hi_x = warp_max(real ? vx : -3.0e38f), hi_y = warp_max(real ? vy : -3.0e38f);
+          const float hm = warp_max(real ? p.lw2[(size_t)prob * strideP + q] : kNegBig);
+          if (lane == 0) {
+            const int gt = (q0 >> 5) + tile;
+            p.tbox[(size_t)prob * ntile + gt] = make_float4(lo_x, lo_y, hi_x, hi_y);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) p.hmax[((size_t)prob * 4 + a) * ntile + gt] = hm;
+          }
+        }
+      }
     }
   }
   grid.sync();
@@ -535,7 +752,7 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
       for (int i = lane; i < N; i += 32) acc += (double)__ldcg(term + i);
       for (int j = lane; j < M; j += 32) {
         const RowFinal f = row_final(__ldcg(potS + p.nqMax + j), __ldcg(potC + p.nqMax + j), b.rho, eps_last);
-        const long long g = cell_index(b, false, b.cu_m[img] + j, slot);
+        const long long g = cell_index(b, false, b.cu_m[img] + __ldcg(p.perm + (size_t)prob * strideP + p.nqMax + j), slot);
         const float wg = b.wt ? b.wt[g] : __fdiv_rn(1.0f, (float)M);
         acc += (double)wg * (double)f.term;
       }
@@ -549,7 +766,7 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
 
 struct StreamPlan {
   int strideP, nqMax, nbx, nby, upp, R;
-  size_t off_pts, off_lw, off_pot, off_h, off_term, off_ctr, off_done, off_sched, off_rounds, total;
+  size_t off_pts, off_lw, off_pot, off_h, off_term, off_perm, off_jb, off_tbox, off_hmax, off_ctr, off_done, off_sched, off_rounds, total;
 };
 
 static int rows_per_lane(int D) { return D <= 2 ? KDOT_STREAM_R2 : (D <= 8 ? 2 : 1); }
@@ -557,8 +774,8 @@ static int rows_per_lane(int D) { return D <= 2 ? KDOT_STREAM_R2 : (D <= 8 ? 2 :
 StreamPlan plan_stream(int nimg, int max_n, int max_m, int B, int D) {
   StreamPlan s;
   s.R = rows_per_lane(D);
-  s.nqMax = (max_n + 3) & ~3;
-  const int mq = (max_m + 3) & ~3;
+  s.nqMax = (max_n + 31) & ~31;  // both clouds start on a 32-point tile boundary (tile boxes / tile maxima of h)
+  const int mq = (max_m + 31) & ~31;
   s.strideP = s.nqMax + mq;
   s.nbx = (max_n + 32 * s.R - 1) / (32 * s.R);
   s.nby = (max_m + 32 * s.R - 1) / (32 * s.R);
@@ -571,6 +788,10 @@ StreamPlan plan_stream(int nimg, int max_n, int max_m, int B, int D) {
   s.off_pot = o;    o = up(o + nprob * 2 * P * 4);
   s.off_h = o;      o = up(o + nprob * 4 * P * 4);
   s.off_term = o;   o = up(o + nprob * P * 4);
+  s.off_perm = o;   o = up(o + nprob * P * 4);
+  s.off_jb = o;     o = up(o + nprob * 2 * P * 4);
+  s.off_tbox = o;   o = up(o + nprob * (P / 32) * 16);
+  s.off_hmax = o;   o = up(o + nprob * 4 * (P / 32) * 4);
   s.off_ctr = o;    o = up(o + (size_t)KDOT_MAX_ROUNDS * 4);
   s.off_done = o;   o = up(o + nprob * 4);
   s.off_sched = o;  o = up(o + (size_t)nimg * KDOT_MAX_ROUNDS * sizeof(RoundConst));
@@ -616,6 +837,10 @@ cudaError_t launch_stream(const SinkhornParams& prm, int D, int max_n, int max_m
   sp.pot = (float*)(base + pl.off_pot);
   sp.h = (float*)(base + pl.off_h);
   sp.term = (float*)(base + pl.off_term);
+  sp.perm = (int*)(base + pl.off_perm);
+  sp.jb = (int*)(base + pl.off_jb);
+  sp.tbox = (float4*)(base + pl.off_tbox);
+  sp.hmax = (float*)(base + pl.off_hmax);
   sp.ctr = (unsigned int*)(base + pl.off_ctr);
   sp.done = (unsigned int*)(base + pl.off_done);
   if (prm.sp.p == 1.0) return D == 2 ? launch_stream_t<2, KDOT_STREAM_R2, true>(sp, stream) : cudaErrorInvalidValue;
@@ -631,3 +856,4 @@ cudaError_t launch_stream(const SinkhornParams& prm, int D, int max_n, int max_m
 }
 
 }  // namespace kdot
+
