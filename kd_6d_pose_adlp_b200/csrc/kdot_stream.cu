@@ -6,13 +6,13 @@
 //
 //   phase 0a  per image: in-place normalisation, bounding box, float64 epsilon schedule
 //   phase 0b  stage every (image, slot) problem once into an L2-resident SoA scratch  pts[prob][d][P], lw[prob][P],
-//             h^S/h^C[prob][2][P]  (coalesced, 16-byte aligned column chunks, pads carry h = -big)
-//   rounds    all problems advance in lock-step (grid barrier per round).  A round is a flat queue of WARP units
-//             (problem, row cloud, 32*R-row block, column set); warps of the persistent grid pull units from a
-//             global counter, so the chip stays balanced for any number / size of problems.  A warp streams the
-//             unit's columns straight from L1/L2 with uniform (broadcast) 128-bit loads -- no shared memory, no
-//             intra-CTA barrier -- and evaluates the pairs exactly like the tiled kernel: direct differences,
-//             log2-domain soft-min argument, lazily re-based online max, one ex2 per pair, packed f32x2 math.
+//             h^S/h^C[prob][2][P]  (32-point tiles, pads carry h = -big); D = 2 clouds in Morton order with per-tile
+//             bounding boxes, which the cold rounds use to skip -- exactly -- tiles whose exponentials all flush to 0
+//   rounds    dataflow, no barrier between rounds: one global FIFO of WARP units (round, problem, row cloud,
+//             32*R-row block, column set); a unit of round r starts when every unit of round r-1 of ITS problem has
+//             finished (per-problem counters).  A warp streams the unit's columns through a private double-buffered
+//             cp.async tile and evaluates the pairs like the tiled kernel: direct differences, log2-domain soft-min
+//             argument, lazily re-based reference exponent, one ex2 per pair, packed f32x2 math.
 //   final     fixed-order fp64 reduction of the per-row loss terms (bit-reproducible).
 //
 // Potentials never leave the chip's L2 between rounds; the N x M cost matrix is never materialised.
