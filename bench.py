@@ -469,6 +469,9 @@ def main():
 
     roofline["traffic"] = ncu_traffic_bytes(roofline["kernel"], args.workload)
     roofline["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/)"
+    if roofline["kernel"] == "kdot_stream_kernel":
+        roofline["traffic_note"] = ("includes the write-back / re-fetch of the kernel's L2-resident scratch (staged clouds, potentials, "
+                                    "tile maxima: ~50 B per point) under ncu's cache control; < 0.2 % of HBM bandwidth, the kernel is SFU/FP32 bound")
 
     # end to end through the host-buffer C-ABI call
     e2e_dt, h2d, d2h, mean_loss = host_e2e(batch, local_rank, args.steps, args.warmup, barrier, cfg)
