@@ -50,11 +50,10 @@ struct StreamParams {
   float* lw2;    // [nprob][strideP]
   float* pot;    // [nprob][2][strideP]          S, C
   float* h;      // [nprob][2 buffers][2][strideP]
-  float* term;   // [nprob][strideP]             weight * loss term of every row (final round)
   int* perm;     // [nprob][strideP]             staged position -> cell index inside its cloud (-1 for pads)
   float4* tbox;  // [nprob][strideP/32]          bounding box (min x, min y, max x, max y) of every 32-point tile (D = 2)
   float* hmax;   // [nprob][2 buffers][2][strideP/32]  max of h over the tile, maintained by the units that write h
-  int* jb;       // [nprob][2][strideP]          per row and column set (own, cross): first column of the chunk that held
+  unsigned short* jb;  // [nprob][2][strideP]  (value = sub-tile index = column / 32)          per row and column set (own, cross): first column of the chunk that held
                  //                              the row's running max in the previous round (seeds the next sweep)
   unsigned int* ctr;  // [KDOT_MAX_ROUNDS]       first 8 bytes: 64-bit head of the global unit FIFO
   unsigned int* done; // [nprob]                 finished units per problem (all rounds)
@@ -363,8 +362,8 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   const float* hCc = hSc + strideP;
   float* hSn = p.h + ((size_t)prob * 4 + (cur ^ 1) * 2) * strideP;
   float* hCn = hSn + strideP;
-  int* jbS = p.jb + (size_t)prob * 2 * strideP;  // indexed by staged row position, like the potentials
-  int* jbC = jbS + strideP;
+  unsigned short* jbS = p.jb + (size_t)prob * 2 * strideP;  // indexed by staged row position, like the potentials
+  unsigned short* jbC = jbS + strideP;
   const int ntile = strideP >> 5;
   const float4* tbox = p.tbox + (size_t)prob * ntile;
   const float* hmSc = p.hmax + ((size_t)prob * 4 + cur * 2) * ntile;  // same layout as h, one value per 32 points
@@ -385,7 +384,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
       for (int d = 0; d < D; ++d) st[0].nx[d] = -pts[(size_t)d * strideP + src];
       TileSkip ts{};
       if (kSkip) {
-        const int jb1[1] = {__ldcg(jbS + src)};
+        const int jb1[1] = {32 * (int)__ldcg(jbS + src)};
         urow_seed<D, 1, true, P1>(st, pts, strideP, hSc, rc.coef, jb1);
         ts.tbox = tbox; ts.hmax = hmSc;
       }
@@ -397,7 +396,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
       for (int d = 0; d < D; ++d) gS[d] = (st[0].g[d].x + st[0].g[d].y) / sS;
       urow_reset<D, 1, true>(st, -1.0f / rc.coef);
       if (kSkip) {
-        const int jb1[1] = {__ldcg(jbC + src)};
+        const int jb1[1] = {32 * (int)__ldcg(jbC + src)};
         urow_seed<D, 1, true, P1>(st, pts + p.nqMax, strideP, hCc + p.nqMax, rc.coef, jb1);
         ts.tbox = tbox + (p.nqMax >> 5); ts.hmax = hmCc + (p.nqMax >> 5);
       }
@@ -410,7 +409,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
       const float gfac = rho < 0.0 ? 1.f : (float)((rho + 0.5 * (double)rc.eps) / rho) * lam;
       const long long g = cell_index(b, true, b.cu_n[img] + p.perm[(size_t)prob * strideP + i], slot);
       const float wg = b.ws ? b.ws[g] : __fdiv_rn(1.0f, (float)N);
-      p.term[(size_t)prob * strideP + i] = wg * f.term;
+      hSn[i] = wg * f.term;  // per-row loss terms go to the h buffer the last round no longer needs
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         float gv = wg * gfac * (f.eS * gS[d] - f.eC * ((st[0].g[d].x + st[0].g[d].y) / sC));
@@ -439,7 +438,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   }
   // warm rounds (eps >= eps_0 / 256): reference exponent folded into the distance chain (one op less per pair)
   const float eps0 = b.sched[(size_t)img * KDOT_MAX_ROUNDS].eps;
-  int* jbArr = own ? jbS : jbC;
+  unsigned short* jbArr = own ? jbS : jbC;
   if (!P1 && rc.eps * 256.0f >= eps0) {
     stream_rows<D, R, false, !P1, false, false>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane);
   } else {
@@ -447,7 +446,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
     if (kSkip) {
       int jbv[R];
 #pragma unroll
-      for (int k = 0; k < R; ++k) jbv[k] = __ldcg(jbArr + (ridx[k] >= 0 ? ridx[k] : rbase));
+      for (int k = 0; k < R; ++k) jbv[k] = 32 * (int)__ldcg(jbArr + (ridx[k] >= 0 ? ridx[k] : rbase));
       urow_seed<D, R, false, P1>(st, cpts, strideP, ch, rc.coef, jbv);
       ts.tbox = tbox + ((cols_x ? 0 : p.nqMax) >> 5);
       ts.hmax = (own ? hmSc : hmCc) + ((cols_x ? 0 : p.nqMax) >> 5);
@@ -472,7 +471,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     if (ridx[k] < 0) continue;
-    if (kSkip) jbArr[ridx[k]] = st[k].jb;
+    if (kSkip) jbArr[ridx[k]] = (unsigned short)(st[k].jb >> 5);
     const float lse = st[k].mref + lg2_approx(st[k].s.x + st[k].s.y);
     float* pot = own ? potS : potC;
     const float nv = rc.scale * lse;
@@ -663,7 +662,6 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
         hb[q] = l2; hb[strideP + q] = l2; hb[2 * strideP + q] = l2; hb[3 * strideP + q] = l2;
         p.pot[(size_t)prob * 2 * strideP + q] = 0.f;
         p.pot[(size_t)prob * 2 * strideP + strideP + q] = 0.f;
-        p.term[(size_t)prob * strideP + q] = 0.f;
         p.perm[(size_t)prob * strideP + q] = real ? i : -1;
         p.jb[(size_t)prob * 2 * strideP + q] = 0;
         p.jb[(size_t)prob * 2 * strideP + strideP + q] = 0;
@@ -745,7 +743,7 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
     double tot = 0.0;
     for (int slot = 0; slot < B; ++slot) {
       const int prob = img * B + slot;
-      const float* term = p.term + (size_t)prob * strideP;
+      const float* term = p.h + ((size_t)prob * 4 + (((nrounds - 1) & 1) ^ 1) * 2) * strideP;  // see stream_unit (last round)
       const float* potS = p.pot + (size_t)prob * 2 * strideP;
       const float* potC = potS + strideP;
       double acc = 0.0;
@@ -766,7 +764,7 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
 
 struct StreamPlan {
   int strideP, nqMax, nbx, nby, upp, R;
-  size_t off_pts, off_lw, off_pot, off_h, off_term, off_perm, off_jb, off_tbox, off_hmax, off_ctr, off_done, off_sched, off_rounds, total;
+  size_t off_pts, off_lw, off_pot, off_h, off_perm, off_jb, off_tbox, off_hmax, off_ctr, off_done, off_sched, off_rounds, total;
 };
 
 static int rows_per_lane(int D) { return D <= 2 ? KDOT_STREAM_R2 : (D <= 8 ? 2 : 1); }
@@ -787,9 +785,8 @@ StreamPlan plan_stream(int nimg, int max_n, int max_m, int B, int D) {
   s.off_lw = o;     o = up(o + nprob * P * 4);
   s.off_pot = o;    o = up(o + nprob * 2 * P * 4);
   s.off_h = o;      o = up(o + nprob * 4 * P * 4);
-  s.off_term = o;   o = up(o + nprob * P * 4);
   s.off_perm = o;   o = up(o + nprob * P * 4);
-  s.off_jb = o;     o = up(o + nprob * 2 * P * 4);
+  s.off_jb = o;     o = up(o + nprob * 2 * P * 2);
   s.off_tbox = o;   o = up(o + nprob * (P / 32) * 16);
   s.off_hmax = o;   o = up(o + nprob * 4 * (P / 32) * 4);
   s.off_ctr = o;    o = up(o + (size_t)KDOT_MAX_ROUNDS * 4);
@@ -836,9 +833,8 @@ cudaError_t launch_stream(const SinkhornParams& prm, int D, int max_n, int max_m
   sp.lw2 = (float*)(base + pl.off_lw);
   sp.pot = (float*)(base + pl.off_pot);
   sp.h = (float*)(base + pl.off_h);
-  sp.term = (float*)(base + pl.off_term);
   sp.perm = (int*)(base + pl.off_perm);
-  sp.jb = (int*)(base + pl.off_jb);
+  sp.jb = (unsigned short*)(base + pl.off_jb);
   sp.tbox = (float4*)(base + pl.off_tbox);
   sp.hmax = (float*)(base + pl.off_hmax);
   sp.ctr = (unsigned int*)(base + pl.off_ctr);
