@@ -1,17 +1,17 @@
-// Fused OT distillation loss, tiled kernel for large clouds (N_i + M_i up to a few thousand, D = 2).
+// Fused OT distillation loss, CTA-resident ("tiled") kernel for mid-size clouds (33..256 points per image, D = 2;
+// anything that fits 227 KB of shared memory with KDOT_FORCE_PATH=tiled).
 //
 // Replaces the same reference code as kdot_small.cu (losses/loss_libs.py:8-12,22-50 + geomloss'
-// tensorized Sinkhorn divergence + its autograd backward) for the dense configurations
-// (every cell of the 1360 / 1364-cell student / teacher grids, BASELINE.json configs 3-5).
+// tensorized Sinkhorn divergence + its autograd backward).
 //
 // Launch 1 (kdot_prep_kernel, one CTA per image): in-place normalisation, image-wide bounding box,
-//   geomloss' float64 epsilon schedule -> per-round fp32 constants in HBM scratch.
-// Launch 2 (kdot_tiled_kernel, one CTA per (image, slot)): the whole cloud [student | teacher] of that
-//   slot is staged ONCE in shared memory as SoA columns (x[], y[], h^S[], h^C[]); every lane owns R rows
-//   and streams all columns with broadcast LDS.128, evaluating |x_i - y_j|^2, the log2-domain
-//   soft-min argument, a lazily rescaled online max and the exp2 sum entirely in registers with packed
-//   f32x2 arithmetic.  The N x M cost matrix is never materialised; HBM traffic is the inputs once
-//   and the gradients once.  Bound: SFU ex2 (1 per pair) / FP32 pipe -- see DESIGN.md.
+//   geomloss' float64 epsilon schedule -> per-round fp32 constants in HBM scratch, rank of the image by size.
+// Launch 2 (kdot_tiled_kernel, one CTA per (image, slot), largest images first): the whole cloud
+//   [student | teacher] of that slot is staged ONCE in shared memory as SoA columns (x[], y[], h^S[], h^C[]); every
+//   lane owns kRows rows and streams all columns with broadcast LDS.128, evaluating |x_i - y_j|^2, the log2-domain
+//   soft-min argument, a lazily rescaled online max and the exp2 sum entirely in registers with packed f32x2
+//   arithmetic; one __syncthreads per Sinkhorn round.  The N x M cost matrix is never materialised; HBM traffic is
+//   the inputs once and the gradients once.  Bound: SFU ex2 (1 per pair) / FP32 pipe -- see DESIGN.md.
 #include "kdot_common.cuh"
 
 namespace kdot {
