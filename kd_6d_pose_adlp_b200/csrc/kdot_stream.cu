@@ -176,6 +176,34 @@ __device__ __forceinline__ void stream_chunk(URow<D, R, GRAD> (&st)[R], const fl
   }
 }
 
+// Speculative form of stream_chunk for the potential-only sweeps: no per-chunk overflow test, the sums are checked once
+// per 32-column sub-tile by the caller (which re-runs the sub-tile through stream_chunk when a sum left the safe range).
+template <int D, int R, bool FOLD>
+__device__ __forceinline__ void stream_chunk_spec(URow<D, R, false> (&st)[R], const float4 (&X)[D], const float4& H,
+                                                  const float2 coef2) {
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    float2 q0 = st[k].mu, q1 = st[k].mu;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float2 nd = make_float2(st[k].nx[d], st[k].nx[d]);
+      const float2 a0 = __fadd2_rn(make_float2(X[d].x, X[d].y), nd);
+      const float2 a1 = __fadd2_rn(make_float2(X[d].z, X[d].w), nd);
+      q0 = (!FOLD && d == 0) ? __fmul2_rn(a0, a0) : __ffma2_rn(a0, a0, q0);
+      q1 = (!FOLD && d == 0) ? __fmul2_rn(a1, a1) : __ffma2_rn(a1, a1, q1);
+    }
+    float2 e0 = __ffma2_rn(q0, coef2, make_float2(H.x, H.y));
+    float2 e1 = __ffma2_rn(q1, coef2, make_float2(H.z, H.w));
+    if (!FOLD) {
+      const float2 nm = make_float2(-st[k].mref, -st[k].mref);
+      e0 = __fadd2_rn(e0, nm);
+      e1 = __fadd2_rn(e1, nm);
+    }
+    st[k].s = __fadd2_rn(st[k].s, make_float2(ex2_approx(e0.x), ex2_approx(e0.y)));
+    st[k].s = __fadd2_rn(st[k].s, make_float2(ex2_approx(e1.x), ex2_approx(e1.y)));
+  }
+}
+
 // Column tile staged per warp in shared memory with cp.async (L2 -> smem, no registers, no L1): T columns of the D
 // coordinate arrays plus the soft-min offsets, double buffered, so the loads of tile t+1 are in flight during the
 // whole evaluation of tile t (thousands of cycles: the L2 latency is fully hidden).
@@ -258,13 +286,36 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
         for (int k = 0; k < R; ++k) st[k].s0 = st[k].s.x + st[k].s.y;
       }
       const int je = min(sb + 32, n);
-#pragma unroll 1
-      for (int j = sb; j < je; j += 4) {
-        float4 X[D];
+      bool redo = true;
+      if (!GRAD && !P1 && D <= 2) {  // speculate: whole sub-tile without overflow tests, one check at the end (larger D: registers)
+        float2 sv[R];
 #pragma unroll
-        for (int d = 0; d < D; ++d) X[d] = *reinterpret_cast<const float4*>(tb + d * T + j);
-        const float4 H = *reinterpret_cast<const float4*>(tb + D * T + j);
-        stream_chunk<D, R, GRAD, FOLD, P1>(st, X, H, coef2, inv_ncoef, big);
+        for (int k = 0; k < R; ++k) sv[k] = st[k].s;
+#pragma unroll 2
+        for (int j = sb; j < je; j += 4) {
+          float4 X[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) X[d] = *reinterpret_cast<const float4*>(tb + d * T + j);
+          const float4 H = *reinterpret_cast<const float4*>(tb + D * T + j);
+          stream_chunk_spec<D, R, FOLD>(reinterpret_cast<URow<D, R, false>(&)[R]>(st), X, H, coef2);
+        }
+        redo = false;
+#pragma unroll
+        for (int k = 0; k < R; ++k) redo |= !(st[k].s.x + st[k].s.y <= big);
+        if (redo) {
+#pragma unroll
+          for (int k = 0; k < R; ++k) st[k].s = sv[k];
+        }
+      }
+      if (redo) {
+#pragma unroll 1
+        for (int j = sb; j < je; j += 4) {
+          float4 X[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) X[d] = *reinterpret_cast<const float4*>(tb + d * T + j);
+          const float4 H = *reinterpret_cast<const float4*>(tb + D * T + j);
+          stream_chunk<D, R, GRAD, FOLD, P1>(st, X, H, coef2, inv_ncoef, big);
+        }
       }
       if (SKIP) {
 #pragma unroll
