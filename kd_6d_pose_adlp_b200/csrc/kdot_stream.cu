@@ -291,7 +291,7 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
         float2 sv[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) sv[k] = st[k].s;
-#pragma unroll 2
+#pragma unroll 4
         for (int j = sb; j < je; j += 4) {
           float4 X[D];
 #pragma unroll
