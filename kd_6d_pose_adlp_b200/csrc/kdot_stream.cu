@@ -226,7 +226,9 @@ __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_g
 // bounds every soft-min argument of the row against the tile's columns from above; when it lies more than 140 below the
 // row's reference exponent for EVERY row of the warp, each ex2 of the tile would flush to exactly +0 in every lane
 // (128 = ex2.approx.ftz flush point, 12 more for the fp32 rounding of the bound), so the tile is skipped without
-// evaluating a single pair.  The result is bit-identical to evaluating it.
+// evaluating a single pair.  Intended to be bit-identical to evaluating it (only exact zeros are dropped); checked by an
+// A/B against a -DKDOT_NO_TILE_SKIP build (tools/ab_tile_skip.py: identical bits on three synthetic workloads), not by
+// the parity tests.
 struct TileSkip {
   const float4* tbox;  // first tile of the column set: (min x, min y, max x, max y)
   const float* hmax;   // same tiles, current h buffer
@@ -260,8 +262,13 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
     __syncwarp();
     const float* tb = wsm + (t & 1) * (D + 1) * T;
     const int n = min(T, ncols - t * T);
+#ifndef KDOT_NO_TILE_SKIP
+    constexpr bool kTileSkip = true;
+#else
+    constexpr bool kTileSkip = false;  // A/B build: same order, seeds and arithmetic, every tile evaluated
+#endif
     unsigned int dead = 0u;  // bit s: 32-column sub-tile s of this tile contributes exactly nothing to any row of the warp
-    if (SKIP && D == 2) {
+    if (SKIP && D == 2 && kTileSkip) {
 #pragma unroll
       for (int sb = 0; sb < T / 32; ++sb) {
         if (sb * 32 >= n) break;
