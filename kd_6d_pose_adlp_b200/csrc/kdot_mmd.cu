@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kMmdThreads) kdot_mmd_kernel(MmdParams p) {
         for (int k = 0; k < cnt; ++k) {
           const long long gk = (long long)(c0 + k) * sc + (long long)slot * ss;
           float q = 0.f, df[kMmdMaxD];
-          for (int d = 0; d < D; ++d) { df[d] = xi[d] - __ldg(rbase + (size_t)D * gk + d) * inv_blur; q = fmaf(df[d], df[d], q); }
+          for (int d = 0; d < D; ++d) { df[d] = xi[d] - rbase[(size_t)D * gk + d] * inv_blur; q = fmaf(df[d], df[d], q); }
           const float wk = rw ? __ldg(rw + gk) : __fdiv_rn(1.0f, (float)cnt);
           float g;
           const float kv = mmd_kernel(p.kind, q, inv_blur, g);
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kMmdThreads) kdot_mmd_kernel(MmdParams p) {
         for (int j = 0; j < M; ++j) {
           const long long gj = (long long)(m0 + j) * b.s_cell_m + (long long)slot * b.s_slot_m;
           float q = 0.f, df[kMmdMaxD];
-          for (int d = 0; d < D; ++d) { df[d] = xi[d] - __ldg(b.xt + (size_t)D * gj + d) * inv_blur; q = fmaf(df[d], df[d], q); }
+          for (int d = 0; d < D; ++d) { df[d] = xi[d] - b.xt[(size_t)D * gj + d] * inv_blur; q = fmaf(df[d], df[d], q); }
           const float wj = b.wt ? __ldg(b.wt + gj) : __fdiv_rn(1.0f, (float)M);
           float g;
           const float kv = mmd_kernel(p.kind, q, inv_blur, g);

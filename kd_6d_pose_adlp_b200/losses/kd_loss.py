@@ -39,16 +39,56 @@ def flatten_head_outputs(pred_cls, pred_reg):
     return cls_f, reg_f
 
 
+def _num_gpus() -> int:
+    """``losses/loss.py:42-43`` (``get_num_gpus``): the process count comes from the launcher's ``WORLD_SIZE``."""
+    return int(os.environ["WORLD_SIZE"]) if "WORLD_SIZE" in os.environ else 1
+
+
 def _reduce_sum_int(value: int, device) -> int:
-    """``losses/loss.py:45-51``: sum of the positive count over ranks (WORLD_SIZE from the env)."""
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world <= 1:
+    """``losses/loss.py:45-51`` (``reduce_sum``): sum of the positive count over ranks.  Like the reference the
+    decision is taken on ``WORLD_SIZE``; unlike it, a launcher environment without an initialised process group
+    (e.g. a single rank started under torchrun for debugging) returns the local value instead of raising."""
+    if _num_gpus() <= 1:
         return value
     import torch.distributed as dist
 
+    if not (dist.is_available() and dist.is_initialized()):
+        return value
     t = torch.tensor([value], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return int(t.item())
+
+
+def _reference_visualizer(pred_xy, pred_t_xy, s_cls, t_cls, step, vis_dir, pos_s, pos_t, losses):
+    """The reference's debug scatter plots (``losses/kd_loss.py:88-89,96-97`` -> ``tools/visualizer.py``), called with
+    the in-place-normalised key-points exactly as there.  Resolved from the integrating repository at call time; when
+    ``tools.visualizer`` (matplotlib) is not importable the plots are skipped -- they are a side effect, not a result."""
+    try:
+        from tools.visualizer import vis_pxpy_post_train, vis_pxpy_post_train_weight
+    except Exception:
+        return False
+    if s_cls is not None:
+        vis_pxpy_post_train_weight(pred_xy, pred_t_xy, s_cls.reshape(-1, 1), t_cls.reshape(-1, 1), step, save_dir=vis_dir,
+                                   pos_per_img_1=pos_s, pos_per_img_2=pos_t, loss=losses)
+    else:
+        vis_pxpy_post_train(pred_xy, pred_t_xy, step, save_dir=vis_dir, pos_per_img_1=pos_s, pos_per_img_2=pos_t,
+                            loss=losses)
+    return True
+
+
+def _status_error(valid_host, where):
+    """Turn a negative per-image kernel status (``include/kdot.h`` KDOT_IMG_*) into an exception.  geomloss raises in
+    the same situations (``epsilon_schedule`` on a zero diameter); the kernel writes NaN and a status instead, so
+    without this check the NaN would reach the optimizer silently."""
+    from .._lib import KdotError
+
+    names = {-1: "KDOT_IMG_DEGENERATE (all key-points of the image coincide: zero diameter)",
+             -2: "KDOT_IMG_TOO_MANY_ROUNDS (epsilon schedule longer than KDOT_MAX_ROUNDS; scaling too close to 1)"}
+    bad = [(i, int(v)) for i, v in enumerate(valid_host) if v < 0]
+    if bad:
+        i, v = bad[0]
+        raise KdotError(f"{where}: image {i} of the mini-batch has status {names.get(v, v)}; "
+                        f"{len(bad)} image(s) affected, their loss and gradients are NaN")
 
 
 def make_kd_pose_loss(base):
@@ -70,7 +110,11 @@ def make_kd_pose_loss(base):
                     self.step = 0
                     self.vis_dir = cfg_kd["vis_dir"] + "/vis"
                     os.makedirs(self.vis_dir, exist_ok=True)
-            self.visualizer = None  # optional callable(pred_xy, pred_t_xy, s_cls, t_cls, step, ...)
+            # callable(pred_xy, pred_t_xy, s_cls, t_cls, step, vis_dir, pos_s, pos_t, losses); None disables the plots
+            self.visualizer = _reference_visualizer
+            # per-image kernel status of the previous step: checked at the start of the next one (no extra host sync
+            # in the step itself); KDOT_SYNC_STATUS=1 checks right after the launch instead
+            self._pending_status = None
 
         # -- the 3-D regression loss of kd_loss.py:52-71 (not the hot path; same math, stock torch ops) -----
         def _object_space_reg_loss(self, pred_xy, target_3d, cls_labels):
@@ -125,22 +169,36 @@ def make_kd_pose_loss(base):
             n_valid = sum(1 for n, m in zip(pos_s, pos_t) if n > 0 and m > 0)
             # pred_xy / xt are normalised in place by the kernel (loss_libs.py:8-12): the visualiser below and
             # any later reader of pred_t['post_kp_2d'] see the normalised values, as with the reference.
-            loss_per_img, _valid, _nits = OTLossFunction.apply(
+            loss_per_img, valid, _nits = OTLossFunction.apply(
                 pred_xy.view(-1, 8, 2), s_cls, xt, t_cls, pos_s, pos_t, self.kd_loss.config,
                 float(self.w), float(self.h), True)
+            if os.environ.get("KDOT_SYNC_STATUS", "0") == "1":
+                _status_error(valid.cpu().tolist(), "KDPoseLoss")
+            else:
+                self._pending_status = valid
             if self.visualizer is not None and hasattr(self, "step") and (self.step == 0 or (self.step + 1) % 1000 == 0):
-                self.visualizer(pred_xy.detach(), xt.view(-1, 2), s_cls, t_cls, self.step, self.vis_dir, pos_s, pos_t)
+                keep = [i for i, (n, m) in enumerate(zip(pos_s, pos_t)) if n > 0 and m > 0]
+                self.visualizer(pred_xy.detach(), xt.view(-1, 2), s_cls, t_cls, self.step, self.vis_dir, pos_s, pos_t,
+                                [loss_per_img[i].detach() for i in keep])
             if n_valid > 0:
                 loss_kd = loss_per_img.sum() / n_valid  # skipped images contribute exactly 0
             else:
-                loss_kd = torch.tensor(0.0, device=pred.device)
+                # kd_loss.py:99-103: no image has both student and teacher cells -> a constant 0 on the device
+                loss_kd = torch.tensor(0.0, device=pred_xy.device)
 
             if weight is not None and weight.sum() > 0:
                 return (losses * weight).sum()
             assert losses.numel() != 0
             return losses.sum(), loss_kd
 
+        def check_status(self):
+            """Raise if the previous step's kernel reported a degenerate image (see ``_status_error``)."""
+            pending, self._pending_status = getattr(self, "_pending_status", None), None
+            if pending is not None:
+                _status_error(pending.cpu().tolist(), "KDPoseLoss (previous step)")
+
         def __call__(self, pred_cls, pred_reg, targets, anchors, pred_t):
+            self.check_status()
             labels, reg_targets, aux_raw_boxes, aux_3d, aux_bbox_trans = self.prepare_targets(targets, anchors)
             self.batch_size = len(labels)
             self.h = 480  # full-image size, not the 256 crop (kd_loss.py:116-117)
@@ -168,7 +226,7 @@ def make_kd_pose_loss(base):
 
             if pos_inds.numel() > 0:
                 self.pos_per_img = pos_per_img
-                if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+                if _num_gpus() <= 1:
                     assert sum(self.pos_per_img) == total_num_pos
                 cls_label = labels_flat[pos_inds] - 1
                 if self.target_coder.target_type != "3D":

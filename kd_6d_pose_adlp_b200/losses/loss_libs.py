@@ -7,6 +7,8 @@ kernel launch for the whole mini-batch.
 """
 from __future__ import annotations
 
+import os
+
 from ..ops import OTLossFunction, normalize_in_place
 from ..samples_loss import SamplesLoss
 
@@ -30,8 +32,17 @@ def kd_loss_2d(pred_xy, target_xy, pred_cls, target_cls, w, h, level, kd_loss, d
         normalize_in_place(target_xy, w, h)
     pos_per_img = [int(v) for v in pos_per_img]
     pos_per_img_t = [int(v) for v in pos_per_img_t]
-    loss_per_img, _valid, _nits = OTLossFunction.apply(
+    loss_per_img, valid, nits = OTLossFunction.apply(
         pred_xy.view(-1, 8, dim), pred_cls, target_xy.view(-1, 8, dim), target_cls,
         pos_per_img, pos_per_img_t, kd_loss.config, float(w), float(h), False)
+    # Per-image kernel status (include/kdot.h KDOT_IMG_*): a degenerate image (all key-points coincide) or an
+    # epsilon schedule longer than KDOT_MAX_ROUNDS yields NaN loss and gradients for that image where geomloss would
+    # raise.  The status stays on the device (no host sync here); it is left on the solver object, and
+    # KDOT_SYNC_STATUS=1 turns it into an exception right away.
+    kd_loss.last_valid, kd_loss.last_nits = valid, nits
+    if os.environ.get("KDOT_SYNC_STATUS", "0") == "1":
+        from .kd_loss import _status_error
+
+        _status_error(valid.cpu().tolist(), "kd_loss_2d")
     keep = [i for i, (n, m) in enumerate(zip(pos_per_img, pos_per_img_t)) if n > 0 and m > 0]
     return [loss_per_img[i] for i in keep]

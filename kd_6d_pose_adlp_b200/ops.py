@@ -113,6 +113,19 @@ def ot_loss_batched(xs, ws, xt, wt, pos_per_img, pos_per_img_t, cfg: OTConfig = 
         cu_n, cu_m = cu_d[:nimg + 1], cu_d[nimg + 1:]
     max_n = max(pos_per_img) if nimg else 0
     max_m = max(pos_per_img_t) if nimg else 0
+    if sum_n == 0 or sum_m == 0:
+        # No image has both a student and a teacher cell: the reference's loop skips every image
+        # (losses/loss_libs.py:25-28) but has already normalised both key-point tensors in place (:8-12).
+        # An empty tensor has no device address to hand to the C entry, so this case is settled here.
+        if normalize:
+            scale = torch.tensor([w, h], dtype=torch.float32, device=dev)
+            for t in (xs, xt):
+                if t.numel():
+                    t.div_(scale)
+        zf = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+        zi = torch.zeros(nimg, dtype=torch.int32, device=dev)
+        return dict(loss_per_img=zf(nimg), loss_per_slot=zf(nimg, B) if want_slots else None, valid=zi,
+                    grad_xs=torch.zeros_like(xs), grad_ws=zf(*xs.shape[:2]), nits=zi.clone())
     # outputs are views of two allocations (16-byte aligned segments) instead of six
     r4 = lambda v: (v + 3) & ~3
     n_gx, n_gw, n_l, n_s = xs.numel(), sum_n * B, nimg, (nimg * B if want_slots else 0)

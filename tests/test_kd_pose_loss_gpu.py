@@ -81,3 +81,76 @@ def test_losses_and_gradients_match_reference():
         assert abs(got_c.sum() - z["gall_cls_sum"][l]) <= 1e-4 * z["gall_cls_abs"][l]
         assert abs(np.abs(got_c).sum() - z["gall_cls_abs"][l]) <= 1e-4 * z["gall_cls_abs"][l]
     assert loss_fn.step == 1 if hasattr(loss_fn, "step") else True
+
+
+def _loss_fn_and_inputs():
+    """The golden scenario's loss object, anchors and student head outputs on cuda:0 (replayed target assignment)."""
+    from kd_6d_pose_adlp_b200.losses.kd_loss import make_kd_pose_loss
+    from kd_6d_pose_adlp_b200.target_coder import TargetCoder, grid_anchors
+
+    z = np.load(GOLDEN)
+    nimg, seed = int(z["nimg"]), int(z["seed"])
+    s_cls, s_reg = scenario.make_head_outputs(nimg, S_HW, seed + 200, teacher=False, target_seed=seed)
+    dev = torch.device("cuda:0")
+    cells = z["cells_per_img"].tolist()
+    split = lambda a: list(torch.split(torch.from_numpy(a).to(dev), cells))
+    doubles.ReplayBase.recorded = dict(labels=split(z["labels"]), reg_targets=split(z["reg_targets"]),
+                                       aux_raw_boxes=split(z["aux_raw_boxes"]), aux_3d=split(z["aux_3d"]),
+                                       aux_bbox_trans=split(z["aux_bbox_trans"]))
+    KDPoseLoss = make_kd_pose_loss(doubles.ReplayBase)
+    loss_fn = KDPoseLoss(2.0, 0.25, scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES, "SSC", 10, 1.0, 9,
+                         scenario.INTERNAL_K, scenario.MESH_DIAMETERS,
+                         TargetCoder("POINT", scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES, target_type="3D"),
+                         dict(scenario.CFG_KD))
+    lv_anchors = grid_anchors(S_HW, scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES, device=dev)
+    pc = [torch.from_numpy(a).to(dev).requires_grad_(True) for a in s_cls]
+    pr = [torch.from_numpy(a).to(dev).requires_grad_(True) for a in s_reg]
+    return z, nimg, dev, loss_fn, [lv_anchors for _ in range(nimg)], pc, pr
+
+
+def test_teacher_selects_nothing_in_every_image():
+    """ref kd_loss.py:99-103: when no image has both student and teacher cells the KD loss is a constant 0
+    (``torch.tensor(0.).cuda()``) and training goes on with the other two losses."""
+    z, nimg, dev, loss_fn, anchors, pc, pr = _loss_fn_and_inputs()
+    pred_t = {"post_kp_2d": torch.zeros(0, 8, 2, device=dev), "post_kp_cls": torch.zeros(0, 8, device=dev),
+              "post_pos_per_img": [0] * nimg}
+    cls_loss, reg_loss, kd_loss = loss_fn(pc, pr, None, anchors, pred_t)
+    assert float(kd_loss) == 0.0 and kd_loss.device.type == "cuda" and not kd_loss.requires_grad
+    assert abs(float(cls_loss) - float(z["cls_loss"])) <= 2e-5 * abs(float(z["cls_loss"]))
+    assert abs(float(reg_loss) - float(z["reg_loss"])) <= 2e-5 * abs(float(z["reg_loss"]))
+    (cls_loss + reg_loss).backward()
+    assert all(torch.isfinite(t.grad).all() for t in pc + pr)
+
+
+def test_kd_loss_2d_with_an_all_empty_side():
+    """ref loss_libs.py:8-12,25-28: both key-point tensors are still normalised in place, every image is skipped."""
+    from kd_6d_pose_adlp_b200 import SamplesLoss
+    from kd_6d_pose_adlp_b200.losses.loss_libs import kd_loss_2d
+
+    dev = torch.device("cuda:0")
+    xy = (torch.rand(3 * 8, 2, device=dev) * 400.0).requires_grad_(True)
+    work = xy * 1.0
+    before = work.detach().clone()
+    cls = torch.rand(3, 8, device=dev)
+    out = kd_loss_2d(work, torch.zeros(0, 2, device=dev), cls, torch.zeros(0, 8, device=dev), 640, 480, "point",
+                     SamplesLoss("sinkhorn", p=2.0, blur=0.001, scaling=0.5, reach=0.5), dim=2,
+                     pos_per_img=[2, 1], pos_per_img_t=[0, 0])
+    assert out == []
+    assert torch.equal(work.detach(), before / torch.tensor([640.0, 480.0], device=dev))
+
+
+def test_degenerate_image_raises_instead_of_feeding_nan(monkeypatch):
+    """A zero-diameter image (all key-points coincide): geomloss' epsilon_schedule raises; the kernel reports
+    KDOT_IMG_DEGENERATE and KDPoseLoss turns it into an exception (immediately with KDOT_SYNC_STATUS=1, else at the
+    next step)."""
+    from kd_6d_pose_adlp_b200 import SamplesLoss, _lib
+    from kd_6d_pose_adlp_b200.losses.loss_libs import kd_loss_2d
+
+    dev = torch.device("cuda:0")
+    monkeypatch.setenv("KDOT_SYNC_STATUS", "1")
+    xy = torch.full((2 * 8, 2), 100.0, device=dev)
+    txy = torch.full((3 * 8, 2), 100.0, device=dev)
+    with pytest.raises(_lib.KdotError, match="DEGENERATE"):
+        kd_loss_2d(xy, txy, torch.rand(2, 8, device=dev) + 0.1, torch.rand(3, 8, device=dev) + 0.1, 640, 480, "point",
+                   SamplesLoss("sinkhorn", p=2.0, blur=0.001, scaling=0.5, reach=0.5), dim=2,
+                   pos_per_img=[2], pos_per_img_t=[3])
