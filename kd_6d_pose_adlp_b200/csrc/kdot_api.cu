@@ -38,7 +38,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 static size_t device_smem_limit_hint();
 // Kernel families (crossovers measured with tools/size_sweep.py on B200):
-//   SMALL   D = 2, p = 2, N + M <= 32 points per image, B <= 16: one warp per (image, slot), all in registers
+//   SMALL   D = 2, p = 2, N + M <= 32 points per image, B <= 8 (or even B <= 16): one warp per (image, slot), all in registers
 //   TILED   D = 2, p = 2, N + M <= kTiledMaxPoints: one CTA per (image, slot), cloud resident in shared memory,
 //           CTA barrier between rounds (1.2-2x faster than the streaming kernel for 33..256 points)
 //   STREAM  everything else (any size, D in {1,2,3,4,8,16}, p = 1): cooperative persistent kernel, chip-wide FIFO
@@ -46,7 +46,9 @@ static size_t device_smem_limit_hint();
 enum KernelPath { PATH_SMALL = 0, PATH_TILED = 1, PATH_STREAM = 2 };
 constexpr int kTiledMaxPoints = 256;
 
-static bool small_path(int max_n, int max_m, int B, int D = 2) { return D == 2 && max_n + max_m <= 32 && B <= 16; }
+static bool small_path(int max_n, int max_m, int B, int D = 2) {
+  return D == 2 && max_n + max_m <= 32 && (B <= 8 || (B <= 16 && B % 2 == 0));  // <= 8 slots (warps) per CTA, see launch_small
+}
 
 static KernelPath choose_path(int max_n, int max_m, int B, int D, float p) {
   if (p != 2.0f) return PATH_STREAM;

@@ -13,17 +13,55 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kNegBig = -1.0e30f;  // "minus infinity" that survives (a - b) without NaN
 constexpr float kLogZeroWeight = -100000.0f;  // geomloss log_weights(): log(0) stand-in
 
-// Per-round constants of the eps-scaling loop, derived in float64 and rounded once.
+// Per-round constants of the eps-scaling loop, derived in float64; the fp32 copies are rounded once.
 //   v_ij (log2 domain) = h_j + coef * |x_i - y_j|^2          coef  = -0.5*log2(e)/eps      (p = 2)
 //                      = h_j + coef * |x_i - y_j|            coef  = -log2(e)/eps          (p = 1)
 //   new potential      = scale * log2-sum-exp                 scale = -lambda(eps)*eps*ln 2
 //   h_j for NEXT round = lw2_j + pot_j * hmul                 hmul  = log2(e)/eps_next
+// Precision plan: potentials, h and the log-sum-exp of EVERY round are carried in float64
+// (per-row work, a few DP operations per row and round); the per-pair soft-min arguments are evaluated in fp32 except
+// in the last KDOT_HI_ROUNDS rounds, where |h| and |coef * d^2| reach 1e3..1e4 log2-units and an fp32 argument
+// (ulp ~1e-3) would leave ~7e-4 relative noise on the soft-max weights of the gradient: there the argument
+// h_j + coef * d^2 - ref is formed in float64 (DADD/DFMA at 64 lanes/clk/SM on B200) and only the small difference is
+// rounded to fp32 for the one ex2 per pair.
 struct RoundConst {
   float coef;
   float scale;
   float hmul;
   float eps;
+  double coefd;
+  double scaled;
+  double hmuld;
 };
+
+#ifndef KDOT_HI_ROUNDS
+#define KDOT_HI_ROUNDS 6
+#endif
+// Rounds [nrounds - KDOT_HI_ROUNDS, nrounds) (the last one is the gradient round) evaluate their pair arguments in
+// float64 -- but only while they are COLD (eps < eps_0 / 256): in a warm round |coef * d^2| <= 0.72 * eps_0 / eps < 185
+// log2-units, where an fp32 argument is accurate to ~1e-5 anyway.  Errors made in earlier rounds are halved by every
+// averaged update that follows, so six trailing rounds leave less than 2^-6 of an fp32 potential's rounding error.
+__device__ __forceinline__ bool is_hi_round(int r, int nrounds, float eps, float eps0) {
+  return r >= nrounds - KDOT_HI_ROUNDS && eps * 256.0f < eps0;
+}
+
+// float64 -> fp32 of a soft-min argument difference without the XU pipe (F2F.F32.F64 shares it with MUFU.EX2 at 16
+// lanes/clk/SM): a 64-bit integer add of half an fp32 ulp (round to nearest, ties away) and three integer-pipe
+// operations that re-pack sign, exponent and the top 23 mantissa bits.  Valid for 2^-126 <= |u| < 2^127; smaller |u|
+// (in particular an exact 0) returns 0.
+__device__ __forceinline__ float f64_to_f32_trunc(double u) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(u) + 0x10000000ull;  // + 2^28: half of the dropped 29 bits
+  const unsigned int hi = (unsigned int)(b >> 32), lo = (unsigned int)b;
+  const unsigned int packed = __funnelshift_l(lo, hi, 3) ^ 0x40000000u;          // exponent re-biased: 11 -> 8 bits
+  const unsigned int bits = (packed & 0x7fffffffu) | (hi & 0x80000000u);
+  return ((hi & 0x7ff00000u) < (897u << 20)) ? 0.f : __uint_as_float(bits);
+}
+// truncating variant without the small-|u| guard, for callers that keep u away from 0 by construction (u <= -1)
+__device__ __forceinline__ float f64_to_f32_trunc_nz(double u) {
+  const unsigned int hi = (unsigned int)__double2hiint(u), lo = (unsigned int)__double2loint(u);
+  const unsigned int packed = __funnelshift_l(lo, hi, 3) ^ 0x40000000u;
+  return __uint_as_float((packed & 0x7fffffffu) | (hi & 0x80000000u));
+}
 
 // data-independent schedule inputs, precomputed in float64 on the host
 struct SchedParams {
@@ -104,6 +142,41 @@ __device__ __forceinline__ float lg2_approx(float x) {
   return y;
 }
 
+// log2 of a running exp-sum in float64.  lg2.approx is accurate to 2^-22 ABSOLUTE only near 1; for a sum kept against
+// a stale reference exponent (up to 2^24 in the tiled kernel, 2^80 in the streaming kernel) its 2^-22 RELATIVE error
+// would put up to 2e-5 log2-units into the potential -- times eps_r / eps_next = 4 in the next round's h.  Splitting
+// off the binary exponent first keeps the SFU argument in [1, 2).
+__device__ __forceinline__ double lg2_sum(float s) {
+  const int bits = __float_as_int(s);
+  const int e = (bits >> 23) - 127;
+  const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+  return (double)e + (double)lg2_approx(m);
+}
+
+// Same to float64 accuracy, for the kernels whose rows hold many pairs (per-row cost: ~15 DP operations): one Newton
+// step on the SFU estimate y0, log2(m) = y0 + log2(m * 2^-y0), with 2^-y0 from a degree-10 float64 polynomial.  In the
+// dense configurations an lse error of 2^-22 per row and round (lg2.approx) alone costs 2e-5 on d/dx.
+__device__ __forceinline__ double lg2_sum_exact(float s) {
+  const int bits = __float_as_int(s);
+  const int e = (bits >> 23) - 127;
+  const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+  const float y0 = lg2_approx(m);
+  const double t = (0.5 - (double)y0) * 0.6931471805599453;  // |t| <= 0.3466
+  double q = 2.7557319223985893e-07;                         // 1/10!
+  q = fma(q, t, 2.7557319223985888e-06);
+  q = fma(q, t, 2.4801587301587302e-05);
+  q = fma(q, t, 1.9841269841269841e-04);
+  q = fma(q, t, 1.3888888888888889e-03);
+  q = fma(q, t, 8.3333333333333332e-03);
+  q = fma(q, t, 4.1666666666666664e-02);
+  q = fma(q, t, 1.6666666666666666e-01);
+  q = fma(q, t, 0.5);
+  q = fma(q, t, 1.0);
+  q = fma(q, t, 1.0);                                        // e^t = 2^(0.5 - y0)
+  const double r = fma((double)m * 0.7071067811865476, q, -1.0);  // m * 2^-y0 - 1  (~1e-7)
+  return ((double)e + (double)y0) + r * 1.4426950408889634 * (1.0 - 0.5 * r);
+}
+
 // geomloss max_diameter on fp32 data: |maxs - mins|_2 evaluated without FMA contraction.
 __device__ __forceinline__ float bbox_diameter(float minx, float miny, float maxx, float maxy) {
   const float ex = __fsub_rn(maxx, minx), ey = __fsub_rn(maxy, miny);
@@ -178,9 +251,12 @@ __device__ __forceinline__ RoundConst make_round_const(int r, const ImgSched& is
   const double eps_next = schedule_eps(round_to_sched(r + 1, is.nits), is, sp);
   const double lam = sp.rho < 0.0 ? 1.0 : 1.0 / (1.0 + eps / sp.rho);
   RoundConst rc;
-  rc.coef = (float)((sp.p == 2.0 ? -0.5 : -1.0) * 1.4426950408889634 / eps);  // cost |d|^2/2 (p = 2) or |d| (p = 1)
-  rc.scale = (float)(-lam * eps * 0.6931471805599453);
-  rc.hmul = (float)(1.4426950408889634 / eps_next);
+  rc.coefd = (sp.p == 2.0 ? -0.5 : -1.0) * 1.4426950408889634 / eps;  // cost |d|^2/2 (p = 2) or |d| (p = 1)
+  rc.scaled = -lam * eps * 0.6931471805599453;
+  rc.hmuld = 1.4426950408889634 / eps_next;
+  rc.coef = (float)rc.coefd;
+  rc.scale = (float)rc.scaled;
+  rc.hmul = (float)rc.hmuld;
   rc.eps = (float)eps;
   return rc;
 }
@@ -205,6 +281,21 @@ __device__ __forceinline__ RowFinal row_final(float S, float C, double rho, floa
     f.eS = expf(-S / r);
     f.eC = expf(-C / r);
     f.term = -k * f.eS * expm1f((S - C) / r);
+  }
+  return f;
+}
+// same with the final potentials in float64: the difference S - C is formed before rounding
+__device__ __forceinline__ RowFinal row_final(double S, double C, double rho, float eps) {
+  RowFinal f;
+  if (rho < 0.0) {
+    f.term = (float)(C - S);
+    f.eS = 1.f;
+    f.eC = 1.f;
+  } else {
+    const float r = (float)rho, k = (float)(rho + 0.5 * (double)eps);
+    f.eS = expf(-(float)S / r);
+    f.eC = expf(-(float)C / r);
+    f.term = -k * f.eS * expm1f((float)(S - C) / r);
   }
   return f;
 }

@@ -25,13 +25,14 @@ namespace kdot {
 
 constexpr int kFastMaxCols = 40;  // padded columns of the fast path (<= 32 points + padding)
 constexpr int kFastMaxCH = kFastMaxCols / 4;
+constexpr int kFastWarpDoubles = (4 + 32 + 3) * kFastMaxCols;  // per-warp shared memory in units of 8 bytes (see the kernel)
 
 // =========================================================================================================
 // fast path
 // =========================================================================================================
 template <int CH, bool GRAD>
 struct RoundOut {
-  float lseX, lseY;        // log2-sum-exp over the student / teacher columns
+  double lseX, lseY;       // log2-sum-exp over the student / teacher columns: (double)max + (double)log2(sum)
   float gXx, gXy, sX;      // sum e * (p_j - p_i) over the student columns and sum e   (GRAD only)
   float gYx, gYy, sY;
 };
@@ -78,47 +79,129 @@ __device__ __forceinline__ RoundOut<CH, GRAD> fast_round(const float* __restrict
   }
   RoundOut<CH, GRAD> o;
   o.sX = sX.x + sX.y; o.sY = sY.x + sY.y;
-  o.lseX = mX + lg2_approx(o.sX);
-  o.lseY = mY + lg2_approx(o.sY);
+  o.lseX = (double)mX + lg2_sum(o.sX);  // the sum is formed in float64: |max| reaches 1e4 in the cold rounds
+  o.lseY = (double)mY + lg2_sum(o.sY);
   o.gXx = gXx.x + gXx.y; o.gXy = gXy.x + gXy.y;
   o.gYx = gYx.x + gYx.y; o.gYy = gYy.x + gYy.y;
   return o;
 }
 
+// High-precision round (the cold ones among the last KDOT_HI_ROUNDS rounds, see kdot_common.cuh): the soft-min argument
+//   t_ij = h_j + coef * |p_i - p_j|^2   (|h|, |coef d^2| ~ 1e3..1e4, t - max_j t = O(1) for the pairs that matter)
+// is formed in float64 from float64 copies of the columns and offsets; only t - ref is re-packed to fp32 for the
+// exponential.  The reference is the fp32 estimate of the row maximum plus 2 (fast_max: one packed fp32 pass, error
+// ~1e-3), so t - ref <= -1 for every pair: a single float64 sweep, and the difference is never 0 (f64_to_f32_trunc).
+template <int CH>
+__device__ __forceinline__ void fast_max(const float* __restrict__ cx, const float* __restrict__ cy,
+                                         const float* __restrict__ hp, int nchx, float px, float py, float coef,
+                                         float& mX, float& mY) {
+  const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py), coef2 = make_float2(coef, coef);
+  mX = kNegBig; mY = kNegBig;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const float4 X = reinterpret_cast<const float4*>(cx)[c];
+    const float4 Y = reinterpret_cast<const float4*>(cy)[c];
+    const float4 H = reinterpret_cast<const float4*>(hp)[c];
+    const float2 d0 = __fadd2_rn(make_float2(X.x, X.y), npx), d1 = __fadd2_rn(make_float2(X.z, X.w), npx);
+    const float2 e0 = __fadd2_rn(make_float2(Y.x, Y.y), npy), e1 = __fadd2_rn(make_float2(Y.z, Y.w), npy);
+    const float2 v0 = __ffma2_rn(__ffma2_rn(e0, e0, __fmul2_rn(d0, d0)), coef2, make_float2(H.x, H.y));
+    const float2 v1 = __ffma2_rn(__ffma2_rn(e1, e1, __fmul2_rn(d1, d1)), coef2, make_float2(H.z, H.w));
+    const float m4 = fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y));
+    if (c < nchx) mX = fmaxf(mX, m4); else mY = fmaxf(mY, m4);  // warp-uniform
+  }
+}
+
+// d2s: this lane's squared distances to every column in float64, [column][lane] in shared memory (computed once per
+// (image, slot): they do not change between rounds), so a pair costs one LDS.64, one DADD and one DFMA on the DP pipe,
+// three integer operations for the re-packing and the one ex2.
+template <int CH, bool GRAD>
+__device__ __forceinline__ RoundOut<CH, GRAD> hi_round(const double* __restrict__ d2s, const double* __restrict__ hd,
+                                                       const float* __restrict__ cx, const float* __restrict__ cy,
+                                                       int nchx, float pxf, float pyf, double coef, float mX, float mY) {
+  const double refX = (double)mX + 2.0, refY = (double)mY + 2.0;
+  float sX = 0.f, sY = 0.f, gXx = 0.f, gXy = 0.f, gYx = 0.f, gYy = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int j = 4 * c;
+    const bool isx = c < nchx;  // warp-uniform
+    const double ref = isx ? refX : refY;
+    const double2 H0 = *reinterpret_cast<const double2*>(hd + j), H1 = *reinterpret_cast<const double2*>(hd + j + 2);
+    const double u0 = fma(coef, d2s[(j + 0) * 32], H0.x - ref), u1 = fma(coef, d2s[(j + 1) * 32], H0.y - ref);
+    const double u2 = fma(coef, d2s[(j + 2) * 32], H1.x - ref), u3 = fma(coef, d2s[(j + 3) * 32], H1.y - ref);
+    const float e0 = ex2_approx(f64_to_f32_trunc_nz(u0)), e1 = ex2_approx(f64_to_f32_trunc_nz(u1));
+    const float e2 = ex2_approx(f64_to_f32_trunc_nz(u2)), e3 = ex2_approx(f64_to_f32_trunc_nz(u3));
+    const float es = (e0 + e1) + (e2 + e3);
+    if (isx) sX += es; else sY += es;
+    if (GRAD) {
+      const float4 XF = *reinterpret_cast<const float4*>(cx + j);
+      const float4 YF = *reinterpret_cast<const float4*>(cy + j);
+      const float gx = fmaf(e0, XF.x - pxf, fmaf(e1, XF.y - pxf, fmaf(e2, XF.z - pxf, e3 * (XF.w - pxf))));
+      const float gy = fmaf(e0, YF.x - pyf, fmaf(e1, YF.y - pyf, fmaf(e2, YF.z - pyf, e3 * (YF.w - pyf))));
+      if (isx) { gXx += gx; gXy += gy; } else { gYx += gx; gYy += gy; }
+    }
+  }
+  RoundOut<CH, GRAD> o;
+  o.sX = sX; o.sY = sY;
+  o.lseX = refX + lg2_sum(sX);
+  o.lseY = refY + lg2_sum(sY);
+  o.gXx = gXx; o.gXy = gXy; o.gYx = gYx; o.gYy = gYy;
+  return o;
+}
+
 struct FastCtx {
   float* cx; float* cy; float* hb;  // per-warp smem: cx[40], cy[40], hb[2 buffers][2 views][40]
+  double* hbd;   // float64 copy of hb (high-precision rounds)
+  double* d2s;   // [40 columns][32 lanes] float64 squared distances of this lane's point to every column
   int nchx;                         // student chunks (padded student columns / 4)
   bool act, isx;
   int col;                          // padded column slot of this lane's point
   float px, py, wgt, lw2;
+  double lw2d;
 };
 
 // All rounds of one (image, slot) for a compile-time chunk count.  Returns via references the final
-// potentials' outputs.  `rc_lane` holds the constants of round (lane) -- broadcast with shuffles.
+// potentials' outputs.  `mine` holds the constants of round (lane) -- broadcast with shuffles.
+// Potentials live in float64 registers for every round; h is published as an fp32 and a float64 copy.
 template <int CH>
 __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const ImgSched& is, const SinkhornParams& prm,
-                                           RoundConst mine, float& S_out, float& C_out,
+                                           RoundConst mine, double& S_out, double& C_out,
                                            float& gSx, float& gSy, float& gCx, float& gCy, RoundConst& rc_last) {
   const int lane = threadIdx.x & 31;
-  float potS = 0.f, potC = 0.f;
+  const float eps0 = (float)is.eps0;
+  double potS = 0.0, potC = 0.0;
   int cur = 0;
   for (int r = 0; r < nrounds - 1; ++r) {
     if (r >= 32 && (r & 31) == 0)  // schedules longer than 32 rounds: next block of constants
       mine = make_round_const(r + lane, is, prm.sp);
+    const double scaled = __shfl_sync(0xffffffffu, mine.scaled, r & 31);
+    const double hmuld = __shfl_sync(0xffffffffu, mine.hmuld, r & 31);
+    double lseX, lseY;
     const float coef = __shfl_sync(0xffffffffu, mine.coef, r & 31);
-    const float scale = __shfl_sync(0xffffffffu, mine.scale, r & 31);
-    const float hmul = __shfl_sync(0xffffffffu, mine.hmul, r & 31);
+    const float eps = __shfl_sync(0xffffffffu, mine.eps, r & 31);
     const float* hp = c.hb + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
-    const RoundOut<CH, false> o = fast_round<CH, false>(c.cx, c.cy, hp, c.nchx, c.px, c.py, coef);
-    const float nS = scale * (c.isx ? o.lseX : o.lseY);
-    const float nC = scale * (c.isx ? o.lseY : o.lseX);
-    potS = r == 0 ? nS : 0.5f * (potS + nS);
-    potC = r == 0 ? nC : 0.5f * (potC + nC);
+    if (!is_hi_round(r, nrounds, eps, eps0)) {
+      const RoundOut<CH, false> o = fast_round<CH, false>(c.cx, c.cy, hp, c.nchx, c.px, c.py, coef);
+      lseX = o.lseX; lseY = o.lseY;
+    } else {
+      const double coefd = __shfl_sync(0xffffffffu, mine.coefd, r & 31);
+      const double* hpd = c.hbd + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
+      float mX, mY;
+      fast_max<CH>(c.cx, c.cy, hp, c.nchx, c.px, c.py, coef, mX, mY);
+      const RoundOut<CH, false> o = hi_round<CH, false>(c.d2s, hpd, c.cx, c.cy, c.nchx, c.px, c.py, coefd, mX, mY);
+      lseX = o.lseX; lseY = o.lseY;
+    }
+    const double nS = scaled * (c.isx ? lseX : lseY);
+    const double nC = scaled * (c.isx ? lseY : lseX);
+    potS = r == 0 ? nS : 0.5 * (potS + nS);
+    potC = r == 0 ? nC : 0.5 * (potC + nC);
     if (c.act) {
+      const double hS = fma(potS, hmuld, c.lw2d), hC = fma(potC, hmuld, c.lw2d);
       float* hn = c.hb + (cur ^ 1) * (2 * kFastMaxCols);
-      const float hS = fmaf(potS, hmul, c.lw2), hC = fmaf(potC, hmul, c.lw2);
-      hn[c.col] = c.isx ? hS : hC;                   // view 0: what student rows read for this column
-      hn[kFastMaxCols + c.col] = c.isx ? hC : hS;    // view 1: what teacher rows read
+      double* hnd = c.hbd + (cur ^ 1) * (2 * kFastMaxCols);
+      hn[c.col] = (float)(c.isx ? hS : hC);                  // view 0: what student rows read for this column
+      hn[kFastMaxCols + c.col] = (float)(c.isx ? hC : hS);   // view 1: what teacher rows read
+      hnd[c.col] = c.isx ? hS : hC;
+      hnd[kFastMaxCols + c.col] = c.isx ? hC : hS;
     }
     __syncwarp();
     cur ^= 1;
@@ -130,13 +213,29 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
   rc_last.scale = __shfl_sync(0xffffffffu, mine.scale, r & 31);
   rc_last.hmul = 0.f;
   rc_last.eps = __shfl_sync(0xffffffffu, mine.eps, r & 31);
+  rc_last.coefd = __shfl_sync(0xffffffffu, mine.coefd, r & 31);
+  rc_last.scaled = __shfl_sync(0xffffffffu, mine.scaled, r & 31);
+  rc_last.hmuld = 0.0;
+  double lseX, lseY;
+  float sX, sY, gXx, gXy, gYx, gYy;
   const float* hp = c.hb + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
-  const RoundOut<CH, true> o = fast_round<CH, true>(c.cx, c.cy, hp, c.nchx, c.px, c.py, rc_last.coef);
-  S_out = rc_last.scale * (c.isx ? o.lseX : o.lseY);
-  C_out = rc_last.scale * (c.isx ? o.lseY : o.lseX);
+  if (!is_hi_round(r, nrounds, rc_last.eps, eps0)) {
+    const RoundOut<CH, true> o = fast_round<CH, true>(c.cx, c.cy, hp, c.nchx, c.px, c.py, rc_last.coef);
+    lseX = o.lseX; lseY = o.lseY; sX = o.sX; sY = o.sY;
+    gXx = o.gXx; gXy = o.gXy; gYx = o.gYx; gYy = o.gYy;
+  } else {
+    const double* hpd = c.hbd + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
+    float mX, mY;
+    fast_max<CH>(c.cx, c.cy, hp, c.nchx, c.px, c.py, rc_last.coef, mX, mY);
+    const RoundOut<CH, true> o = hi_round<CH, true>(c.d2s, hpd, c.cx, c.cy, c.nchx, c.px, c.py, rc_last.coefd, mX, mY);
+    lseX = o.lseX; lseY = o.lseY; sX = o.sX; sY = o.sY;
+    gXx = o.gXx; gXy = o.gXy; gYx = o.gYx; gYy = o.gYy;
+  }
+  S_out = rc_last.scaled * (c.isx ? lseX : lseY);
+  C_out = rc_last.scaled * (c.isx ? lseY : lseX);
   // barycentric displacements  sum_j W_ij (p_j - p_i)  against own / other cloud (student rows use them)
-  gSx = o.gXx / o.sX; gSy = o.gXy / o.sX;
-  gCx = o.gYx / o.sY; gCy = o.gYy / o.sY;
+  gSx = gXx / sX; gSy = gXy / sX;
+  gCx = gYx / sY; gCy = gYy / sY;
 }
 
 // The B slots of an image are spread over a thread-block cluster of `split` CTAs (B/split warps each) so that a
@@ -144,16 +243,21 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
 // per-sub-partition SFU / FP32 pipes, not by occupancy.  The cluster is only needed twice: a barrier before the
 // in-place normalisation (every CTA reads all slots for the bounding box) and the fixed-order sum over slots,
 // which rank 0 performs on values its peers wrote into its shared memory (DSMEM).
-__global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm, int split) {
+#ifndef KDOT_SMALL_MINBLOCKS
+#define KDOT_SMALL_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(256, KDOT_SMALL_MINBLOCKS) kdot_small_fast_kernel(SinkhornParams prm, int split) {
   cg::cluster_group cluster = cg::this_cluster();
   const int img = blockIdx.x / split, part = blockIdx.x - img * split;
   const int wpc = prm.B / split;  // warps (slots) per CTA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = part * wpc + warp;
   const int B = prm.B;
-  extern __shared__ __align__(16) float s_dynf[];  // per warp: cx[40] | cy[40] | h[2][2][40]
+  // per warp: float64 h[2][2][40] | d2[40][32], then fp32 cx[40] | cy[40] | h[2][2][40]
+  extern __shared__ __align__(16) double s_dynd[];
   __shared__ double s_slot_loss[16];               // rank 0's copy collects all B slots
-  float* wbase_s = s_dynf + (size_t)warp * (6 * kFastMaxCols);
+  double* wbase_d = s_dynd + (size_t)warp * kFastWarpDoubles;
+  float* wbase_s = reinterpret_cast<float*>(wbase_d + (4 + 32) * kFastMaxCols);
 
   const int n0 = prm.cu_n[img], N = prm.cu_n[img + 1] - n0;
   const int m0 = prm.cu_m[img], M = prm.cu_m[img + 1] - m0;
@@ -168,11 +272,12 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
   }
   FastCtx c;
   c.cx = wbase_s; c.cy = wbase_s + kFastMaxCols; c.hb = wbase_s + 2 * kFastMaxCols;
+  c.hbd = wbase_d; c.d2s = wbase_d + 4 * kFastMaxCols + lane;
   c.nchx = Nq >> 2;
   c.act = lane < P;
   c.isx = lane < N;
   c.col = c.isx ? lane : Nq + (lane - N);
-  c.px = c.py = 0.f; c.wgt = 0.f; c.lw2 = 0.f;
+  c.px = c.py = 0.f; c.wgt = 0.f; c.lw2 = 0.f; c.lw2d = 0.0;
 
   // ---- every warp touches only ITS slot: load, normalise in place (the same thread reads and writes an element, so
   //      there is no cross-warp hazard), log-weight.  The image-wide bounding box is assembled from the per-warp
@@ -199,6 +304,7 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
     minx = maxx = v.x;
     miny = maxy = v.y;
     c.lw2 = (c.wgt > 0.f ? logf(c.wgt) : kLogZeroWeight) * kLog2e;
+    c.lw2d = (double)c.lw2;
   }
   float* gx_out = prm.grad_xs + 2 * gidx;
   dbg_stamp(prm, img, 1);
@@ -259,17 +365,26 @@ __global__ void __launch_bounds__(512) kdot_small_fast_kernel(SinkhornParams prm
   // ---- stage this slot's columns: [student | pad | teacher | pad], pads carry h = -big (exp2 -> 0) ----
   for (int j = lane; j < kFastMaxCols; j += 32) {
     c.cx[j] = 0.f; c.cy[j] = 0.f;
-    c.hb[j] = kNegBig; c.hb[kFastMaxCols + j] = kNegBig;
-    c.hb[2 * kFastMaxCols + j] = kNegBig; c.hb[3 * kFastMaxCols + j] = kNegBig;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) { c.hb[v * kFastMaxCols + j] = kNegBig; c.hbd[v * kFastMaxCols + j] = (double)kNegBig; }
   }
   __syncwarp();
   if (c.act) {
     c.cx[c.col] = c.px; c.cy[c.col] = c.py;
     c.hb[c.col] = c.lw2; c.hb[kFastMaxCols + c.col] = c.lw2;  // init round: h = log w for both views
+    c.hbd[c.col] = c.lw2d; c.hbd[kFastMaxCols + c.col] = c.lw2d;
   }
   __syncwarp();
 
-  float S = 0.f, C = 0.f, gSx = 0.f, gSy = 0.f, gCx = 0.f, gCy = 0.f;
+  {  // float64 squared distances of this lane's point to every staged column (pads: columns at the origin, h = -big)
+    const double pxd = (double)c.px, pyd = (double)c.py;
+    for (int j = 0; j < Nq + Mq; ++j) {
+      const double ax = (double)c.cx[j] - pxd, ay = (double)c.cy[j] - pyd;
+      c.d2s[j * 32] = fma(ay, ay, ax * ax);
+    }
+  }
+  double S = 0.0, C = 0.0;
+  float gSx = 0.f, gSy = 0.f, gCx = 0.f, gCy = 0.f;
   RoundConst rc;
   const RoundConst mine = make_round_const(lane, is, prm.sp);  // lane r holds the constants of round r
   dbg_stamp(prm, img, 4);
@@ -328,10 +443,16 @@ cudaError_t launch_small(const SinkhornParams& prm, int max_n, int max_m, cudaSt
       cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
       if (sm_count <= 0) sm_count = 148;
     }
-    int split = 1;
+    int split = prm.B > 8 ? 2 : 1;  // at most 8 warps (slots) per CTA: the kernel is compiled for 256 threads
     while (split < 8 && prm.B % (split * 2) == 0 && (long long)prm.nimg * split * 2 <= (long long)sm_count) split *= 2;
     const int wpc = prm.B / split;
-    const size_t smem = (size_t)wpc * 6 * kFastMaxCols * sizeof(float);
+    const size_t smem = (size_t)wpc * kFastWarpDoubles * sizeof(double);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(kdot_small_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = smem;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(prm.nimg * split);
     cfg.blockDim = dim3(32 * wpc);

@@ -48,8 +48,9 @@ struct StreamParams {
   int upp;       // units per problem per round = 2 * (nbx + nby)
   float* pts;    // [nprob][D][strideP]
   float* lw2;    // [nprob][strideP]
-  float* pot;    // [nprob][2][strideP]          S, C
-  float* h;      // [nprob][2 buffers][2][strideP]
+  double* pot;   // [nprob][2][strideP]          S, C  (float64: kdot_common.cuh precision plan)
+  float* h;      // [nprob][2 buffers][2][strideP]   fp32 head of h (what the fp32 sweeps and the skip test read)
+  float* hlo;    // [nprob][2 buffers][2][strideP]   h - (float)h: float64 h = h + hlo for the high-precision sub-tiles
   int* perm;     // [nprob][strideP]             staged position -> cell index inside its cloud (-1 for pads)
   float4* tbox;  // [nprob][strideP/32]          bounding box (min x, min y, max x, max y) of every 32-point tile (D = 2)
   float* hmax;   // [nprob][2 buffers][2][strideP/32]  max of h over the tile, maintained by the units that write h
@@ -209,8 +210,9 @@ __device__ __forceinline__ void stream_chunk_spec(URow<D, R, false> (&st)[R], co
 // whole evaluation of tile t (thousands of cycles: the L2 latency is fully hidden).
 template <int D>
 __host__ __device__ constexpr int stream_tile_cols() { return D <= 4 ? 128 : (D <= 8 ? 64 : 32); }
+// ... plus a float64 staging area for one 32-column sub-tile (D coordinates + h), see stream_subtile_hi
 template <int D>
-__host__ __device__ constexpr int stream_warp_smem_floats() { return 2 * (D + 1) * stream_tile_cols<D>(); }
+__host__ __device__ constexpr int stream_warp_smem_floats() { return 2 * (D + 1) * stream_tile_cols<D>() + 2 * (D + 1) * 32; }
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
   const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
@@ -234,12 +236,104 @@ struct TileSkip {
   const float* hmax;   // same tiles, current h buffer
 };
 
-// SKIP: cold rounds of D = 2 problems staged in Morton order -- tile-level exact skipping (TileSkip) plus the sub-tile
-// bookkeeping that seeds the next round.
-template <int D, int R, bool GRAD, bool FOLD, bool P1, bool SKIP>
+// ---- high-precision sub-tiles (cold rounds among the last KDOT_HI_ROUNDS, kdot_common.cuh) -------------------------
+// In those rounds |h| and |coef d^2| reach 1e3..1e4 log2-units and an fp32 soft-min argument (ulp ~1e-3) is too coarse
+// for the pairs that carry the sum.  Only few pairs do: the fp32 evaluation of a 32-column sub-tile is kept as a SCREEN,
+// and a sub-tile that adds more than kSigThr of a row's running sum (for any row of the warp) is re-evaluated with the
+// argument  h_j + coef |p_i - p_j|^2 - ref  formed in float64 -- float64 copies of its 32 columns are staged in a small
+// per-warp buffer (coordinates are exact fp32 -> float64 conversions, h = fp32 head + fp32 tail read from L2).
+// What stays fp32 adds up to < 32 * kSigThr per row with ~1e-3 relative error each: < 1e-6 of the sum.
+// The gradient round evaluates every sub-tile it does not skip this way (its weights enter d/dx directly).
+constexpr float kSigThr = 1.0f / 16384.0f;
+
+struct HiArgs {
+  const float* chlo;  // fp32 tail of h for the column set (same indexing as ch)
+  double* hsm;        // per-warp staging: [D + 1][32] float64
+  double coefd;
+};
+
+template <int D>
+__device__ __forceinline__ void stage_hi(double* hsm, const float* tb, int T, int sb, int lane, const float* chlo_sub,
+                                         bool valid) {
+  __syncwarp();  // previous readers of the staging buffer are done
+#pragma unroll
+  for (int d = 0; d < D; ++d) hsm[d * 32 + lane] = (double)tb[d * T + sb + lane];
+  const float lo = valid ? __ldcg(chlo_sub + lane) : 0.f;
+  hsm[D * 32 + lane] = (double)tb[D * T + sb + lane] + (double)lo;
+  __syncwarp();
+}
+
+// The R rows of this lane against the ncol (multiple of 4, <= 32) staged columns; same lazily re-based running sums as
+// stream_chunk (mref stays an fp32 number: it is exactly representable in float64).
+template <int D, int R, bool GRAD>
+__device__ __forceinline__ void stream_subtile_hi(URow<D, R, GRAD> (&st)[R], const double* __restrict__ hsm,
+                                                  const float* __restrict__ tb, int T, int sb, int ncol, double coefd,
+                                                  float inv_ncoef, float big) {
+#pragma unroll 1
+  for (int j = 0; j < ncol; j += 4) {
+    double q[R][4];
+#pragma unroll
+    for (int k = 0; k < R; ++k) { q[k][0] = 0.0; q[k][1] = 0.0; q[k][2] = 0.0; q[k][3] = 0.0; }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double2 A = *reinterpret_cast<const double2*>(hsm + d * 32 + j);
+      const double2 Bv = *reinterpret_cast<const double2*>(hsm + d * 32 + j + 2);
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const double nd = (double)st[k].nx[d];  // -p_i (loop invariant)
+        const double a0 = A.x + nd, a1 = A.y + nd, a2 = Bv.x + nd, a3 = Bv.y + nd;
+        q[k][0] = fma(a0, a0, q[k][0]); q[k][1] = fma(a1, a1, q[k][1]);
+        q[k][2] = fma(a2, a2, q[k][2]); q[k][3] = fma(a3, a3, q[k][3]);
+      }
+    }
+    const double2 H0 = *reinterpret_cast<const double2*>(hsm + D * 32 + j);
+    const double2 H1 = *reinterpret_cast<const double2*>(hsm + D * 32 + j + 2);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const double t0 = fma(coefd, q[k][0], H0.x), t1 = fma(coefd, q[k][1], H0.y);
+      const double t2 = fma(coefd, q[k][2], H1.x), t3 = fma(coefd, q[k][3], H1.y);
+      double mr = (double)st[k].mref;
+      float p0 = ex2_approx(f64_to_f32_trunc(t0 - mr)), p1 = ex2_approx(f64_to_f32_trunc(t1 - mr));
+      float p2 = ex2_approx(f64_to_f32_trunc(t2 - mr)), p3 = ex2_approx(f64_to_f32_trunc(t3 - mr));
+      if (!((p0 + p1) + (p2 + p3) <= big)) {  // cold: re-base on the max of this chunk
+        const float vm = (float)fmax(fmax(t0, t1), fmax(t2, t3));
+        const float sc = ex2_approx(st[k].mref - vm);  // 0 for the first chunk (mref = -big)
+        st[k].s.x *= sc; st[k].s.y *= sc;
+        if (GRAD) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) { st[k].g[d].x *= sc; st[k].g[d].y *= sc; }
+        }
+        st[k].mref = vm;
+        st[k].gbest *= sc;
+        st[k].s0 *= sc;
+        const float mu = vm * inv_ncoef;
+        st[k].mu = make_float2(mu, mu);
+        mr = (double)vm;
+        p0 = ex2_approx(f64_to_f32_trunc(t0 - mr)); p1 = ex2_approx(f64_to_f32_trunc(t1 - mr));
+        p2 = ex2_approx(f64_to_f32_trunc(t2 - mr)); p3 = ex2_approx(f64_to_f32_trunc(t3 - mr));
+      }
+      st[k].s.x += p0 + p2; st[k].s.y += p1 + p3;
+      if (GRAD) {  // weights from the float64 argument, coordinate differences in fp32 (exact enough: they are O(cloud size))
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float4 X = *reinterpret_cast<const float4*>(tb + d * T + sb + j);
+          const float nd = st[k].nx[d];
+          st[k].g[d].x = fmaf(p0, X.x + nd, fmaf(p2, X.z + nd, st[k].g[d].x));
+          st[k].g[d].y = fmaf(p1, X.y + nd, fmaf(p3, X.w + nd, st[k].g[d].y));
+        }
+      }
+    }
+  }
+}
+
+// SEED: cold rounds -- sub-tile bookkeeping that seeds the next round's reference exponent.  TSKIP: D = 2 problems staged
+// in Morton order -- tile-level exact skipping (TileSkip).  HI: high-precision sub-tiles (see above; never with FOLD / P1).
+template <int D, int R, bool GRAD, bool FOLD, bool P1, bool SEED, bool TSKIP, bool HI>
 __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const float* __restrict__ pts, int strideP,
                                             const float* ch, int ncols, float coef, float* wsm, int lane,
-                                            const TileSkip ts = TileSkip{}) {
+                                            const TileSkip ts = TileSkip{}, const HiArgs ha = HiArgs{}) {
+  static_assert(!(HI && (FOLD || P1)), "high-precision sub-tiles exist for the unfolded squared cost only");
+  static_assert(!TSKIP || (D == 2 && SEED), "tile skipping needs the D = 2 tile boxes and a seeded reference");
   constexpr int T = stream_tile_cols<D>();
   const float2 coef2 = make_float2(coef, coef);
   const float inv_ncoef = -1.0f / coef;
@@ -268,7 +362,7 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
     constexpr bool kTileSkip = false;  // A/B build: same order, seeds and arithmetic, every tile evaluated
 #endif
     unsigned int dead = 0u;  // bit s: 32-column sub-tile s of this tile contributes exactly nothing to any row of the warp
-    if (SKIP && D == 2 && kTileSkip) {
+    if (TSKIP && kTileSkip) {
 #pragma unroll
       for (int sb = 0; sb < T / 32; ++sb) {
         if (sb * 32 >= n) break;
@@ -287,44 +381,63 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
     }
 #pragma unroll 1
     for (int sb = 0; sb < n; sb += 32) {
-      if (SKIP && D == 2 && ((dead >> (sb >> 5)) & 1u)) continue;
-      if (SKIP) {
+      if (TSKIP && ((dead >> (sb >> 5)) & 1u)) continue;
+      if (SEED || HI) {
 #pragma unroll
         for (int k = 0; k < R; ++k) st[k].s0 = st[k].s.x + st[k].s.y;
       }
       const int je = min(sb + 32, n);
-      bool redo = true;
-      if (!GRAD && !P1 && D <= 2) {  // speculate: whole sub-tile without overflow tests, one check at the end (larger D: registers)
-        float2 sv[R];
+      if (HI && GRAD) {  // gradient round: float64 arguments for every evaluated sub-tile
+        stage_hi<D>(ha.hsm, tb, T, sb, lane, ha.chlo + t * T + sb, sb + lane < n);
+        stream_subtile_hi<D, R, GRAD>(st, ha.hsm, tb, T, sb, je - sb, ha.coefd, inv_ncoef, big);
+      } else {
+        bool redo = true;
+        if (!GRAD && !P1 && D <= 2) {  // speculate: whole sub-tile without overflow tests, one check at the end (larger D: registers)
+          float2 sv[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) sv[k] = st[k].s;
+          for (int k = 0; k < R; ++k) sv[k] = st[k].s;
 #pragma unroll 4
-        for (int j = sb; j < je; j += 4) {
-          float4 X[D];
+          for (int j = sb; j < je; j += 4) {
+            float4 X[D];
 #pragma unroll
-          for (int d = 0; d < D; ++d) X[d] = *reinterpret_cast<const float4*>(tb + d * T + j);
-          const float4 H = *reinterpret_cast<const float4*>(tb + D * T + j);
-          stream_chunk_spec<D, R, FOLD>(reinterpret_cast<URow<D, R, false>(&)[R]>(st), X, H, coef2);
+            for (int d = 0; d < D; ++d) X[d] = *reinterpret_cast<const float4*>(tb + d * T + j);
+            const float4 H = *reinterpret_cast<const float4*>(tb + D * T + j);
+            stream_chunk_spec<D, R, FOLD>(reinterpret_cast<URow<D, R, false>(&)[R]>(st), X, H, coef2);
+          }
+          redo = false;
+#pragma unroll
+          for (int k = 0; k < R; ++k) redo |= !(st[k].s.x + st[k].s.y <= big);
+          if (redo) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) st[k].s = sv[k];
+          }
         }
-        redo = false;
-#pragma unroll
-        for (int k = 0; k < R; ++k) redo |= !(st[k].s.x + st[k].s.y <= big);
         if (redo) {
-#pragma unroll
-          for (int k = 0; k < R; ++k) st[k].s = sv[k];
-        }
-      }
-      if (redo) {
 #pragma unroll 1
-        for (int j = sb; j < je; j += 4) {
-          float4 X[D];
+          for (int j = sb; j < je; j += 4) {
+            float4 X[D];
 #pragma unroll
-          for (int d = 0; d < D; ++d) X[d] = *reinterpret_cast<const float4*>(tb + d * T + j);
-          const float4 H = *reinterpret_cast<const float4*>(tb + D * T + j);
-          stream_chunk<D, R, GRAD, FOLD, P1>(st, X, H, coef2, inv_ncoef, big);
+            for (int d = 0; d < D; ++d) X[d] = *reinterpret_cast<const float4*>(tb + d * T + j);
+            const float4 H = *reinterpret_cast<const float4*>(tb + D * T + j);
+            stream_chunk<D, R, GRAD, FOLD, P1>(st, X, H, coef2, inv_ncoef, big);
+          }
+        }
+        if (HI) {  // screen: does this sub-tile carry a visible share of any row's sum?
+          bool sig = false;
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            const float sk = st[k].s.x + st[k].s.y;
+            sig |= (sk - st[k].s0) > kSigThr * fmaxf(sk, 1.0f);
+          }
+          if (__any_sync(0xffffffffu, sig)) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) st[k].s = make_float2(st[k].s0, 0.f);  // drop the fp32 contribution (s0 follows re-basing)
+            stage_hi<D>(ha.hsm, tb, T, sb, lane, ha.chlo + t * T + sb, sb + lane < n);
+            stream_subtile_hi<D, R, GRAD>(st, ha.hsm, tb, T, sb, je - sb, ha.coefd, inv_ncoef, big);
+          }
         }
       }
-      if (SKIP) {
+      if (SEED) {
 #pragma unroll
         for (int k = 0; k < R; ++k) {
           const float gain = (st[k].s.x + st[k].s.y) - st[k].s0;
@@ -393,7 +506,9 @@ __device__ __forceinline__ long long cell_index(const SinkhornParams& b, bool st
 // One warp unit: rows [blk*32R, blk*32R + 32R) of one cloud of problem `prob` against one column set, round r.
 template <int D, int R, bool P1>
 __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int prob, int uu, int lane, float* wsm) {
-  constexpr bool kSkip = (D == 2) && !P1;  // exact skipping of all-underflow chunks in the cold rounds (see stream_chunk)
+  constexpr bool kSeed = !P1;                // cold rounds: seeded reference exponent (urow_seed) + sub-tile bookkeeping
+  constexpr bool kTSkip = (D == 2) && !P1;   // exact skipping of all-underflow sub-tiles in the cold rounds (TileSkip)
+  constexpr int T = stream_tile_cols<D>();
   const SinkhornParams& b = p.b;
   const int B = b.B, strideP = p.strideP;
   const int img = prob / B, slot = prob - img * B;
@@ -411,15 +526,22 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   if (blk * 32 * R >= rcount) return;  // padded unit of a smaller image
   const int rbase = rows_x ? 0 : p.nqMax;
   const RoundConst rc = b.sched[(size_t)img * KDOT_MAX_ROUNDS + r];
+  const float eps0 = b.sched[(size_t)img * KDOT_MAX_ROUNDS].eps;
+  const bool warm = !P1 && rc.eps * 256.0f >= eps0;   // reference exponent folded into the distance chain (one op less per pair)
+  const bool hi = !P1 && is_hi_round(r, nrounds, rc.eps, eps0);
   const double rho = b.rho;
   const float* pts = p.pts + (size_t)prob * D * strideP;
   const float* lw2 = p.lw2 + (size_t)prob * strideP;
-  float* potS = p.pot + (size_t)prob * 2 * strideP;
-  float* potC = potS + strideP;
+  double* potS = p.pot + (size_t)prob * 2 * strideP;
+  double* potC = potS + strideP;
   const float* hSc = p.h + ((size_t)prob * 4 + cur * 2) * strideP;
   const float* hCc = hSc + strideP;
   float* hSn = p.h + ((size_t)prob * 4 + (cur ^ 1) * 2) * strideP;
   float* hCn = hSn + strideP;
+  const float* lSc = p.hlo + ((size_t)prob * 4 + cur * 2) * strideP;
+  const float* lCc = lSc + strideP;
+  float* lSn = p.hlo + ((size_t)prob * 4 + (cur ^ 1) * 2) * strideP;
+  float* lCn = lSn + strideP;
   unsigned short* jbS = p.jb + (size_t)prob * 2 * strideP;  // indexed by staged row position, like the potentials
   unsigned short* jbC = jbS + strideP;
   const int ntile = strideP >> 5;
@@ -428,6 +550,9 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   const float* hmCc = hmSc + ntile;
   float* hmSn = p.hmax + ((size_t)prob * 4 + (cur ^ 1) * 2) * ntile;
   float* hmCn = hmSn + ntile;
+  HiArgs ha{};
+  ha.hsm = reinterpret_cast<double*>(wsm + 2 * (D + 1) * T);
+  ha.coefd = rc.coefd;
 
   if (last && rows_x) {
     if (!own) return;  // the student's last round is done by the "own" unit for both column sets
@@ -441,27 +566,33 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
 #pragma unroll
       for (int d = 0; d < D; ++d) st[0].nx[d] = -pts[(size_t)d * strideP + src];
       TileSkip ts{};
-      if (kSkip) {
+      if (kSeed && !warm) {
         const int jb1[1] = {32 * (int)__ldcg(jbS + src)};
         urow_seed<D, 1, true, P1>(st, pts, strideP, hSc, rc.coef, jb1);
         ts.tbox = tbox; ts.hmax = hmSc;
       }
-      stream_rows<D, 1, true, false, P1, kSkip>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane, ts);
+      ha.chlo = lSc;
+      if (hi) stream_rows<D, 1, true, false, P1, kSeed, kTSkip, !P1>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane, ts, ha);
+      else if (!warm) stream_rows<D, 1, true, false, P1, kSeed, kTSkip, false>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane, ts);
+      else stream_rows<D, 1, true, false, P1, false, false, false>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane);
       const float sS = st[0].s.x + st[0].s.y;
-      const float S = rc.scale * (st[0].mref + lg2_approx(sS));
+      const double S = rc.scaled * ((double)st[0].mref + lg2_sum_exact(sS));
       float gS[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) gS[d] = (st[0].g[d].x + st[0].g[d].y) / sS;
       urow_reset<D, 1, true>(st, -1.0f / rc.coef);
-      if (kSkip) {
+      if (kSeed && !warm) {
         const int jb1[1] = {32 * (int)__ldcg(jbC + src)};
         urow_seed<D, 1, true, P1>(st, pts + p.nqMax, strideP, hCc + p.nqMax, rc.coef, jb1);
         ts.tbox = tbox + (p.nqMax >> 5); ts.hmax = hmCc + (p.nqMax >> 5);
       }
-      stream_rows<D, 1, true, false, P1, kSkip>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane, ts);
+      ha.chlo = lCc + p.nqMax;
+      if (hi) stream_rows<D, 1, true, false, P1, kSeed, kTSkip, !P1>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane, ts, ha);
+      else if (!warm) stream_rows<D, 1, true, false, P1, kSeed, kTSkip, false>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane, ts);
+      else stream_rows<D, 1, true, false, P1, false, false, false>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane);
       if (!act) continue;
       const float sC = st[0].s.x + st[0].s.y;
-      const float C = rc.scale * (st[0].mref + lg2_approx(sC));
+      const double C = rc.scaled * ((double)st[0].mref + lg2_sum_exact(sC));
       const RowFinal f = row_final(S, C, rho, rc.eps);
       const float lam = rho < 0.0 ? 1.f : (float)(1.0 / (1.0 + (double)rc.eps / rho));
       const float gfac = rho < 0.0 ? 1.f : (float)((rho + 0.5 * (double)rc.eps) / rho) * lam;
@@ -480,8 +611,9 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   }
 
   const bool cols_x = (rows_x == own);
-  const float* cpts = cols_x ? pts : pts + p.nqMax;
-  const float* ch = (own ? hSc : hCc) + (cols_x ? 0 : p.nqMax);
+  const int coff = cols_x ? 0 : p.nqMax;
+  const float* cpts = pts + coff;
+  const float* ch = (own ? hSc : hCc) + coff;
   const int ncols = cols_x ? Nq : Mq;
   URow<D, R, false> st[R];
   urow_reset<D, R, false>(st, -1.0f / rc.coef);
@@ -494,48 +626,57 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
 #pragma unroll
     for (int d = 0; d < D; ++d) st[k].nx[d] = -pts[(size_t)d * strideP + src];
   }
-  // warm rounds (eps >= eps_0 / 256): reference exponent folded into the distance chain (one op less per pair)
-  const float eps0 = b.sched[(size_t)img * KDOT_MAX_ROUNDS].eps;
   unsigned short* jbArr = own ? jbS : jbC;
-  if (!P1 && rc.eps * 256.0f >= eps0) {
-    stream_rows<D, R, false, !P1, false, false>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane);
+  if (warm) {
+#ifdef KDOT_NO_FOLD
+    constexpr bool kFold = false;  // A/B build
+#else
+    constexpr bool kFold = !P1;
+#endif
+    stream_rows<D, R, false, kFold, false, false, false, false>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane);
   } else {
     TileSkip ts{};
-    if (kSkip) {
+    if (kSeed) {
       int jbv[R];
 #pragma unroll
       for (int k = 0; k < R; ++k) jbv[k] = 32 * (int)__ldcg(jbArr + (ridx[k] >= 0 ? ridx[k] : rbase));
       urow_seed<D, R, false, P1>(st, cpts, strideP, ch, rc.coef, jbv);
-      ts.tbox = tbox + ((cols_x ? 0 : p.nqMax) >> 5);
-      ts.hmax = (own ? hmSc : hmCc) + ((cols_x ? 0 : p.nqMax) >> 5);
+      ts.tbox = tbox + (coff >> 5);
+      ts.hmax = (own ? hmSc : hmCc) + (coff >> 5);
     }
-    stream_rows<D, R, false, false, P1, kSkip>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane, ts);
+    ha.chlo = (own ? lSc : lCc) + coff;
+    if (hi) stream_rows<D, R, false, false, P1, kSeed, kTSkip, !P1>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane, ts, ha);
+    else stream_rows<D, R, false, false, P1, kSeed, kTSkip, false>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane, ts);
   }
-  if (kSkip && !last) {  // per-tile maximum of the h values this unit is about to publish (rows of pass k = one tile)
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-      float hv = kNegBig;
-      if (ridx[k] >= 0) {
-        const float lse = st[k].mref + lg2_approx(st[k].s.x + st[k].s.y);
-        const float nv = rc.scale * lse;
-        const float pv = r == 0 ? nv : 0.5f * (__ldcg((own ? potS : potC) + ridx[k]) + nv);
-        hv = fmaf(pv, rc.hmul, __ldcg(lw2 + ridx[k]));
-      }
-      hv = warp_max(hv);
-      const int tile = (rbase + blk * 32 * R + 32 * k) >> 5;
-      if (lane == 0 && tile < ntile && blk * 32 * R + 32 * k < rcount) (own ? hmSn : hmCn)[tile] = hv;
-    }
-  }
+  // new potentials / next round's h in float64; fp32 head + tail of h, per-tile maximum of the head (skip test)
+  double hv[R];
 #pragma unroll
   for (int k = 0; k < R; ++k) {
+    hv[k] = (double)kNegBig;
     if (ridx[k] < 0) continue;
-    if (kSkip) jbArr[ridx[k]] = (unsigned short)(st[k].jb >> 5);
-    const float lse = st[k].mref + lg2_approx(st[k].s.x + st[k].s.y);
-    float* pot = own ? potS : potC;
-    const float nv = rc.scale * lse;
-    const float pv = (r == 0 || last) ? nv : 0.5f * (__ldcg(pot + ridx[k]) + nv);
+    if (kSeed && !warm) jbArr[ridx[k]] = (unsigned short)(st[k].jb >> 5);
+    // warm rounds fold the reference into the distance chain as mu = fl(mref / -coef): the sums are relative to
+    // -coef * mu, which differs from mref by the rounding of mu (6e-8 |mref|: up to 1e-5) -- add back what was subtracted
+    const double ref = warm ? -(double)rc.coef * (double)st[k].mu.x : (double)st[k].mref;
+    const double lse = ref + lg2_sum_exact(st[k].s.x + st[k].s.y);
+    double* pot = own ? potS : potC;
+    const double nv = rc.scaled * lse;
+    const double pv = (r == 0 || last) ? nv : 0.5 * (__ldcg(pot + ridx[k]) + nv);
     pot[ridx[k]] = pv;
-    if (!last) (own ? hSn : hCn)[ridx[k]] = fmaf(pv, rc.hmul, __ldcg(lw2 + ridx[k]));
+    if (!last) {
+      hv[k] = fma(pv, rc.hmuld, (double)__ldcg(lw2 + ridx[k]));
+      const float hh = (float)hv[k];
+      (own ? hSn : hCn)[ridx[k]] = hh;
+      (own ? lSn : lCn)[ridx[k]] = (float)(hv[k] - (double)hh);
+    }
+  }
+  if (kTSkip && !last) {  // per-tile maximum of the h values this unit publishes (rows of pass k = one tile)
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const float hm = warp_max((float)hv[k]);
+      const int tile = (rbase + blk * 32 * R + 32 * k) >> 5;
+      if (lane == 0 && tile < ntile && blk * 32 * R + 32 * k < rcount) (own ? hmSn : hmCn)[tile] = hm;
+    }
   }
 }
 
@@ -718,8 +859,10 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
         p.lw2[(size_t)prob * strideP + q] = l2;
         float* hb = p.h + (size_t)prob * 4 * strideP;
         hb[q] = l2; hb[strideP + q] = l2; hb[2 * strideP + q] = l2; hb[3 * strideP + q] = l2;
-        p.pot[(size_t)prob * 2 * strideP + q] = 0.f;
-        p.pot[(size_t)prob * 2 * strideP + strideP + q] = 0.f;
+        p.pot[(size_t)prob * 2 * strideP + q] = 0.0;
+        p.pot[(size_t)prob * 2 * strideP + strideP + q] = 0.0;
+        float* lb = p.hlo + (size_t)prob * 4 * strideP;
+        lb[q] = 0.f; lb[strideP + q] = 0.f; lb[2 * strideP + q] = 0.f; lb[3 * strideP + q] = 0.f;
         p.perm[(size_t)prob * strideP + q] = real ? i : -1;
         p.jb[(size_t)prob * 2 * strideP + q] = 0;
         p.jb[(size_t)prob * 2 * strideP + strideP + q] = 0;
@@ -802,8 +945,8 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
     for (int slot = 0; slot < B; ++slot) {
       const int prob = img * B + slot;
       const float* term = p.h + ((size_t)prob * 4 + (((nrounds - 1) & 1) ^ 1) * 2) * strideP;  // see stream_unit (last round)
-      const float* potS = p.pot + (size_t)prob * 2 * strideP;
-      const float* potC = potS + strideP;
+      const double* potS = p.pot + (size_t)prob * 2 * strideP;
+      const double* potC = potS + strideP;
       double acc = 0.0;
       for (int i = lane; i < N; i += 32) acc += (double)__ldcg(term + i);
       for (int j = lane; j < M; j += 32) {
@@ -822,7 +965,7 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
 
 struct StreamPlan {
   int strideP, nqMax, nbx, nby, upp, R;
-  size_t off_pts, off_lw, off_pot, off_h, off_perm, off_jb, off_tbox, off_hmax, off_ctr, off_done, off_sched, off_rounds, total;
+  size_t off_pts, off_lw, off_pot, off_h, off_hlo, off_perm, off_jb, off_tbox, off_hmax, off_ctr, off_done, off_sched, off_rounds, total;
 };
 
 static int rows_per_lane(int D) { return D <= 2 ? KDOT_STREAM_R2 : (D <= 8 ? 2 : 1); }
@@ -841,8 +984,9 @@ StreamPlan plan_stream(int nimg, int max_n, int max_m, int B, int D) {
   size_t o = 0;
   s.off_pts = o;    o = up(o + nprob * D * P * 4);
   s.off_lw = o;     o = up(o + nprob * P * 4);
-  s.off_pot = o;    o = up(o + nprob * 2 * P * 4);
+  s.off_pot = o;    o = up(o + nprob * 2 * P * 8);
   s.off_h = o;      o = up(o + nprob * 4 * P * 4);
+  s.off_hlo = o;    o = up(o + nprob * 4 * P * 4);
   s.off_perm = o;   o = up(o + nprob * P * 4);
   s.off_jb = o;     o = up(o + nprob * 2 * P * 2);
   s.off_tbox = o;   o = up(o + nprob * (P / 32) * 16);
@@ -868,6 +1012,11 @@ static cudaError_t launch_stream_t(StreamParams& sp, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int smem_bytes = (kStreamThreads / 32) * stream_warp_smem_floats<D>() * (int)sizeof(float);
+    if (smem_bytes > 48 * 1024) {
+      cudaError_t ea = cudaFuncSetAttribute(kdot_stream_kernel<D, R, P1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+      if (ea != cudaSuccess) return ea;
+    }
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kdot_stream_kernel<D, R, P1>, kStreamThreads,
                                                                   (kStreamThreads / 32) * stream_warp_smem_floats<D>() * sizeof(float));
     if (e != cudaSuccess) return e;
@@ -889,8 +1038,9 @@ cudaError_t launch_stream(const SinkhornParams& prm, int D, int max_n, int max_m
   sp.strideP = pl.strideP; sp.nqMax = pl.nqMax; sp.nbx = pl.nbx; sp.nby = pl.nby; sp.upp = pl.upp;
   sp.pts = (float*)(base + pl.off_pts);
   sp.lw2 = (float*)(base + pl.off_lw);
-  sp.pot = (float*)(base + pl.off_pot);
+  sp.pot = (double*)(base + pl.off_pot);
   sp.h = (float*)(base + pl.off_h);
+  sp.hlo = (float*)(base + pl.off_hlo);
   sp.perm = (int*)(base + pl.off_perm);
   sp.jb = (unsigned short*)(base + pl.off_jb);
   sp.tbox = (float4*)(base + pl.off_tbox);

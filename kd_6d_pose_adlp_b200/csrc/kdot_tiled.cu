@@ -228,6 +228,66 @@ __device__ __forceinline__ void rows_vs_columns(RowState<kGrad> (&st)[kRows], co
   }
 }
 
+// High-precision sweep (last KDOT_HI_ROUNDS rounds, kdot_common.cuh): same structure, but the soft-min argument
+// t = h_j + coef * |p_i - p_j|^2 - mref is formed in float64 from float64 copies of the columns, offsets and reference;
+// only the small difference is rounded to fp32 for the exponential.  Sums and gradient accumulators stay fp32 (they are
+// sums of positive terms / of terms weighted by exact fp32 coordinate differences).
+template <bool kGrad>
+struct RowStateHi {
+  double px, py;
+  double mref;
+  float pxf, pyf;
+  float2 s;
+  float2 gx, gy;
+};
+
+template <bool kGrad>
+__device__ __forceinline__ void rows_vs_columns_hi(RowStateHi<kGrad>& st, const double* __restrict__ cxd,
+                                                   const double* __restrict__ cyd, const double* __restrict__ chd,
+                                                   const float* __restrict__ cx, const float* __restrict__ cy, int c0,
+                                                   int c1, double coef) {
+  const float big = exp2f(kTau);
+#pragma unroll 1
+  for (int j = c0; j < c1; j += 4) {
+    const double2 X0 = *reinterpret_cast<const double2*>(cxd + j), X1 = *reinterpret_cast<const double2*>(cxd + j + 2);
+    const double2 Y0 = *reinterpret_cast<const double2*>(cyd + j), Y1 = *reinterpret_cast<const double2*>(cyd + j + 2);
+    const double2 H0 = *reinterpret_cast<const double2*>(chd + j), H1 = *reinterpret_cast<const double2*>(chd + j + 2);
+    const double ax0 = X0.x - st.px, ax1 = X0.y - st.px, ax2 = X1.x - st.px, ax3 = X1.y - st.px;
+    const double ay0 = Y0.x - st.py, ay1 = Y0.y - st.py, ay2 = Y1.x - st.py, ay3 = Y1.y - st.py;
+    const double v0 = fma(coef, fma(ay0, ay0, ax0 * ax0), H0.x), v1 = fma(coef, fma(ay1, ay1, ax1 * ax1), H0.y);
+    const double v2 = fma(coef, fma(ay2, ay2, ax2 * ax2), H1.x), v3 = fma(coef, fma(ay3, ay3, ax3 * ax3), H1.y);
+    float p0 = ex2_approx(f64_to_f32_trunc(v0 - st.mref)), p1 = ex2_approx(f64_to_f32_trunc(v1 - st.mref));
+    float p2 = ex2_approx(f64_to_f32_trunc(v2 - st.mref)), p3 = ex2_approx(f64_to_f32_trunc(v3 - st.mref));
+    if (!((p0 + p1) + (p2 + p3) <= big)) {  // cold: re-base on the exact max of this chunk
+      const double vm = fmax(fmax(v0, v1), fmax(v2, v3));
+      const float sc = ex2_approx((float)(st.mref - vm));  // 0 for the first chunk (mref = -big)
+      st.s.x *= sc; st.s.y *= sc;
+      if (kGrad) { st.gx.x *= sc; st.gx.y *= sc; st.gy.x *= sc; st.gy.y *= sc; }
+      st.mref = vm;
+      p0 = ex2_approx(f64_to_f32_trunc(v0 - vm)); p1 = ex2_approx(f64_to_f32_trunc(v1 - vm));
+      p2 = ex2_approx(f64_to_f32_trunc(v2 - vm)); p3 = ex2_approx(f64_to_f32_trunc(v3 - vm));
+    }
+    st.s.x += p0 + p2; st.s.y += p1 + p3;
+    if (kGrad) {
+      const float4 XF = *reinterpret_cast<const float4*>(cx + j);
+      const float4 YF = *reinterpret_cast<const float4*>(cy + j);
+      st.gx.x = fmaf(p0, XF.x - st.pxf, fmaf(p2, XF.z - st.pxf, st.gx.x));
+      st.gx.y = fmaf(p1, XF.y - st.pxf, fmaf(p3, XF.w - st.pxf, st.gx.y));
+      st.gy.x = fmaf(p0, YF.x - st.pyf, fmaf(p2, YF.z - st.pyf, st.gy.x));
+      st.gy.y = fmaf(p1, YF.y - st.pyf, fmaf(p3, YF.w - st.pyf, st.gy.y));
+    }
+  }
+}
+
+template <bool kGrad>
+__device__ __forceinline__ void rows_reset_hi(RowStateHi<kGrad>& st, float pxf, float pyf) {
+  st.px = (double)pxf; st.py = (double)pyf; st.pxf = pxf; st.pyf = pyf;
+  st.mref = (double)kNegBig;
+  st.s = make_float2(0.f, 0.f);
+  st.gx = make_float2(0.f, 0.f);
+  st.gy = make_float2(0.f, 0.f);
+}
+
 template <bool kGrad>
 __device__ __forceinline__ void rows_reset(RowState<kGrad> (&st)[kRows]) {
 #pragma unroll
@@ -255,13 +315,18 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
   const int Nq = round4(N), Mq = round4(M), Pq = Nq + Mq;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
-  extern __shared__ __align__(16) float smem[];
-  float* cx = smem;
+  extern __shared__ __align__(16) double smem_d[];
+  // float64 arrays first (alignment), then the fp32 ones: 8 doubles + 7 floats = 92 bytes per padded point
+  double* cxd = smem_d;
+  double* cyd = cxd + Pq;
+  double* potS = cyd + Pq;
+  double* potC = potS + Pq;
+  double* hSd = potC + Pq;        // [2][Pq]
+  double* hCd = hSd + 2 * Pq;     // [2][Pq]
+  float* cx = reinterpret_cast<float*>(hCd + 2 * Pq);
   float* cy = cx + Pq;
   float* lw2 = cy + Pq;
-  float* potS = lw2 + Pq;
-  float* potC = potS + Pq;
-  float* hS = potC + Pq;          // [2][Pq]
+  float* hS = lw2 + Pq;           // [2][Pq]
   float* hC = hS + 2 * Pq;        // [2][Pq]
   const RoundConst* __restrict__ rcs = prm.sched + (size_t)img * KDOT_MAX_ROUNDS;  // L1/L2-resident, 1 load / round
   __shared__ unsigned int s_ctr[2];
@@ -290,9 +355,12 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
       l2 = (wg > 0.f ? logf(wg) : kLogZeroWeight) * kLog2e;
     }
     cx[q] = v.x; cy[q] = v.y; lw2[q] = l2;
-    potS[q] = 0.f; potC[q] = 0.f;
+    cxd[q] = (double)v.x; cyd[q] = (double)v.y;
+    potS[q] = 0.0; potC[q] = 0.0;
     hS[q] = l2; hC[q] = l2;             // init round: h = log w  (pads: -big => exp2 -> 0)
     hS[Pq + q] = l2; hC[Pq + q] = l2;   // pads of the second buffer stay -big forever
+    hSd[q] = (double)l2; hCd[q] = (double)l2;
+    hSd[Pq + q] = (double)l2; hCd[Pq + q] = (double)l2;
   }
   if (threadIdx.x == 0) { s_ctr[0] = 0u; s_ctr[1] = 0u; }
   __syncthreads();
@@ -303,10 +371,15 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
   int cur = 0;
   for (int r = 0; r < nrounds - 1; ++r) {
     const RoundConst rc = rcs[r];
+    const bool hi = is_hi_round(r, nrounds, rc.eps, rcs[0].eps);
     const float* hSc = hS + cur * Pq;
     const float* hCc = hC + cur * Pq;
     float* hSn = hS + (cur ^ 1) * Pq;
     float* hCn = hC + (cur ^ 1) * Pq;
+    const double* hScd = hSd + cur * Pq;
+    const double* hCcd = hCd + cur * Pq;
+    double* hSnd = hSd + (cur ^ 1) * Pq;
+    double* hCnd = hCd + (cur ^ 1) * Pq;
     const int nunits = 2 * (nbx + nby);
     for (;;) {
       unsigned int u = 0;
@@ -320,29 +393,46 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
       const int rbase = rows_x ? 0 : Nq, rcount = rows_x ? N : M;
       const bool cols_x = (rows_x == own);
       const int c0 = cols_x ? 0 : Nq, c1 = cols_x ? Nq : Pq;
-      const float* ch = own ? hSc : hCc;
 
-      RowState<false> st[kRows];
-      rows_reset(st);
       int ridx[kRows];
+      double lse[kRows];
 #pragma unroll
       for (int k = 0; k < kRows; ++k) {
         const int i = blk * kUnitRows + lane + 32 * k;
         ridx[k] = i < rcount ? rbase + i : -1;
-        const int src = ridx[k] >= 0 ? ridx[k] : rbase;
-        st[k].nx = make_float2(-cx[src], -cx[src]);
-        st[k].ny = make_float2(-cy[src], -cy[src]);
       }
-      rows_vs_columns<false>(st, cx, cy, ch, c0, c1, rc.coef);
+      if (!hi) {
+        RowState<false> st[kRows];
+        rows_reset(st);
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+          const int src = ridx[k] >= 0 ? ridx[k] : rbase;
+          st[k].nx = make_float2(-cx[src], -cx[src]);
+          st[k].ny = make_float2(-cy[src], -cy[src]);
+        }
+        rows_vs_columns<false>(st, cx, cy, own ? hSc : hCc, c0, c1, rc.coef);
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) lse[k] = (double)st[k].mref + lg2_sum_exact(st[k].s.x + st[k].s.y);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+          const int src = ridx[k] >= 0 ? ridx[k] : rbase;
+          RowStateHi<false> sh;
+          rows_reset_hi(sh, cx[src], cy[src]);
+          rows_vs_columns_hi<false>(sh, cxd, cyd, own ? hScd : hCcd, cx, cy, c0, c1, rc.coefd);
+          lse[k] = sh.mref + lg2_sum_exact(sh.s.x + sh.s.y);
+        }
+      }
 #pragma unroll
       for (int k = 0; k < kRows; ++k) {
         if (ridx[k] < 0) continue;
-        const float lse = st[k].mref + lg2_approx(st[k].s.x + st[k].s.y);
-        float* pot = own ? potS : potC;
-        const float nv = rc.scale * lse;
-        const float pv = r == 0 ? nv : 0.5f * (pot[ridx[k]] + nv);
+        double* pot = own ? potS : potC;
+        const double nv = rc.scaled * lse[k];
+        const double pv = r == 0 ? nv : 0.5 * (pot[ridx[k]] + nv);
         pot[ridx[k]] = pv;
-        (own ? hSn : hCn)[ridx[k]] = fmaf(pv, rc.hmul, lw2[ridx[k]]);
+        const double hv = fma(pv, rc.hmuld, (double)lw2[ridx[k]]);
+        (own ? hSn : hCn)[ridx[k]] = (float)hv;
+        (own ? hSnd : hCnd)[ridx[k]] = hv;
       }
     }
     if (threadIdx.x == 0) s_ctr[(r & 1) ^ 1] = 0u;
@@ -354,8 +444,11 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
   {
     const int r = nrounds - 1;
     const RoundConst rc = rcs[r];
+    const bool hi = is_hi_round(r, nrounds, rc.eps, rcs[0].eps);
     const float* hSc = hS + cur * Pq;
     const float* hCc = hC + cur * Pq;
+    const double* hScd = hSd + cur * Pq;
+    const double* hCcd = hCd + cur * Pq;
     float* term = hS + (cur ^ 1) * Pq;  // free buffer: per-row loss terms (weight * term)
     const double rho = prm.rho;
     const float lam = rho < 0.0 ? 1.f : (float)(1.0 / (1.0 + (double)rc.eps / rho));
@@ -368,41 +461,68 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
       if ((int)u >= nunits) break;
       if ((int)u < nbx) {
         // student rows: both column sets in one unit so the gradient is finished in registers
-        RowState<true> st[kRows];
         int ridx[kRows];
-        float S[kRows], gSx[kRows], gSy[kRows];
-        rows_reset(st);
+        double S[kRows], C[kRows];
+        float gSx[kRows], gSy[kRows], gCx[kRows], gCy[kRows];
 #pragma unroll
         for (int k = 0; k < kRows; ++k) {
           const int i = (int)u * kUnitRows + lane + 32 * k;
           ridx[k] = i < N ? i : -1;
-          const int src = ridx[k] >= 0 ? ridx[k] : 0;
-          st[k].nx = make_float2(-cx[src], -cx[src]);
-          st[k].ny = make_float2(-cy[src], -cy[src]);
         }
-        rows_vs_columns<true>(st, cx, cy, hSc, 0, Nq, rc.coef);
+        if (!hi) {
+          RowState<true> st[kRows];
+          rows_reset(st);
 #pragma unroll
-        for (int k = 0; k < kRows; ++k) {
-          const float s = st[k].s.x + st[k].s.y;
-          S[k] = rc.scale * (st[k].mref + lg2_approx(s));
-          gSx[k] = (st[k].gx.x + st[k].gx.y) / s;
-          gSy[k] = (st[k].gy.x + st[k].gy.y) / s;
+          for (int k = 0; k < kRows; ++k) {
+            const int src = ridx[k] >= 0 ? ridx[k] : 0;
+            st[k].nx = make_float2(-cx[src], -cx[src]);
+            st[k].ny = make_float2(-cy[src], -cy[src]);
+          }
+          rows_vs_columns<true>(st, cx, cy, hSc, 0, Nq, rc.coef);
+#pragma unroll
+          for (int k = 0; k < kRows; ++k) {
+            const float s = st[k].s.x + st[k].s.y;
+            S[k] = rc.scaled * ((double)st[k].mref + lg2_sum_exact(s));
+            gSx[k] = (st[k].gx.x + st[k].gx.y) / s;
+            gSy[k] = (st[k].gy.x + st[k].gy.y) / s;
+          }
+          rows_reset(st);
+          rows_vs_columns<true>(st, cx, cy, hCc, Nq, Pq, rc.coef);
+#pragma unroll
+          for (int k = 0; k < kRows; ++k) {
+            const float s = st[k].s.x + st[k].s.y;
+            C[k] = rc.scaled * ((double)st[k].mref + lg2_sum_exact(s));
+            gCx[k] = (st[k].gx.x + st[k].gx.y) / s;
+            gCy[k] = (st[k].gy.x + st[k].gy.y) / s;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < kRows; ++k) {
+            const int src = ridx[k] >= 0 ? ridx[k] : 0;
+            RowStateHi<true> sh;
+            rows_reset_hi(sh, cx[src], cy[src]);
+            rows_vs_columns_hi<true>(sh, cxd, cyd, hScd, cx, cy, 0, Nq, rc.coefd);
+            float s = sh.s.x + sh.s.y;
+            S[k] = rc.scaled * (sh.mref + lg2_sum_exact(s));
+            gSx[k] = (sh.gx.x + sh.gx.y) / s;
+            gSy[k] = (sh.gy.x + sh.gy.y) / s;
+            rows_reset_hi(sh, cx[src], cy[src]);
+            rows_vs_columns_hi<true>(sh, cxd, cyd, hCcd, cx, cy, Nq, Pq, rc.coefd);
+            s = sh.s.x + sh.s.y;
+            C[k] = rc.scaled * (sh.mref + lg2_sum_exact(s));
+            gCx[k] = (sh.gx.x + sh.gx.y) / s;
+            gCy[k] = (sh.gy.x + sh.gy.y) / s;
+          }
         }
-        rows_reset(st);
-        rows_vs_columns<true>(st, cx, cy, hCc, Nq, Pq, rc.coef);
 #pragma unroll
         for (int k = 0; k < kRows; ++k) {
           if (ridx[k] < 0) continue;
-          const float s = st[k].s.x + st[k].s.y;
-          const float C = rc.scale * (st[k].mref + lg2_approx(s));
-          const float gCx = (st[k].gx.x + st[k].gx.y) / s;
-          const float gCy = (st[k].gy.x + st[k].gy.y) / s;
-          const RowFinal f = row_final(S[k], C, rho, rc.eps);
+          const RowFinal f = row_final(S[k], C[k], rho, rc.eps);
           const long long g = (long long)(n0 + ridx[k]) * prm.s_cell_n + (long long)slot * prm.s_slot_n;
           const float wg = prm.ws ? prm.ws[g] : __fdiv_rn(1.0f, (float)N);
           term[ridx[k]] = wg * f.term;
-          float gx = wg * gfac * (f.eS * gSx[k] - f.eC * gCx);
-          float gy = wg * gfac * (f.eS * gSy[k] - f.eC * gCy);
+          float gx = wg * gfac * (f.eS * gSx[k] - f.eC * gCx[k]);
+          float gy = wg * gfac * (f.eS * gSy[k] - f.eC * gCy[k]);
           if (prm.normalize) {
             gx = __fdiv_rn(gx, prm.w);
             gy = __fdiv_rn(gy, prm.h);
@@ -416,22 +536,39 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
         const int blk = ub >> 1;
         const bool own = (ub & 1) == 0;
         const int c0 = own ? Nq : 0, c1 = own ? Pq : Nq;
-        RowState<false> st[kRows];
-        rows_reset(st);
         int ridx[kRows];
+        double lse[kRows];
 #pragma unroll
         for (int k = 0; k < kRows; ++k) {
           const int i = blk * kUnitRows + lane + 32 * k;
           ridx[k] = i < M ? Nq + i : -1;
-          const int src = ridx[k] >= 0 ? ridx[k] : Nq;
-          st[k].nx = make_float2(-cx[src], -cx[src]);
-          st[k].ny = make_float2(-cy[src], -cy[src]);
         }
-        rows_vs_columns<false>(st, cx, cy, own ? hSc : hCc, c0, c1, rc.coef);
+        if (!hi) {
+          RowState<false> st[kRows];
+          rows_reset(st);
+#pragma unroll
+          for (int k = 0; k < kRows; ++k) {
+            const int src = ridx[k] >= 0 ? ridx[k] : Nq;
+            st[k].nx = make_float2(-cx[src], -cx[src]);
+            st[k].ny = make_float2(-cy[src], -cy[src]);
+          }
+          rows_vs_columns<false>(st, cx, cy, own ? hSc : hCc, c0, c1, rc.coef);
+#pragma unroll
+          for (int k = 0; k < kRows; ++k) lse[k] = (double)st[k].mref + lg2_sum_exact(st[k].s.x + st[k].s.y);
+        } else {
+#pragma unroll
+          for (int k = 0; k < kRows; ++k) {
+            const int src = ridx[k] >= 0 ? ridx[k] : Nq;
+            RowStateHi<false> sh;
+            rows_reset_hi(sh, cx[src], cy[src]);
+            rows_vs_columns_hi<false>(sh, cxd, cyd, own ? hScd : hCcd, cx, cy, c0, c1, rc.coefd);
+            lse[k] = sh.mref + lg2_sum_exact(sh.s.x + sh.s.y);
+          }
+        }
 #pragma unroll
         for (int k = 0; k < kRows; ++k) {
           if (ridx[k] < 0) continue;
-          (own ? potS : potC)[ridx[k]] = rc.scale * (st[k].mref + lg2_approx(st[k].s.x + st[k].s.y));
+          (own ? potS : potC)[ridx[k]] = rc.scaled * lse[k];
         }
       }
     }
@@ -469,7 +606,7 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
 
 size_t tiled_smem_bytes(int max_n, int max_m) {
   const size_t pq = (size_t)((max_n + 3) & ~3) + (size_t)((max_m + 3) & ~3);
-  return pq * 9 * sizeof(float);
+  return pq * (8 * sizeof(double) + 7 * sizeof(float));
 }
 
 cudaError_t launch_tiled(const SinkhornParams& prm, int max_n, int max_m, cudaStream_t stream, size_t smem_limit,
