@@ -387,6 +387,69 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def allreduce_leg(dev, bench, barrier, max_over_ranks, world, rank):
+    """The exchange a data-parallel run adds around the path (reference strategy
+    train_kd.py:50,137 + libs/train_libs.py:124-130): NCCL all-reduce of the student's gradient bucket, in place on
+    the persistent flat buffer of kd_6d_pose_adlp_b200.dist.GradBucket, plus the two-scalar loss exchange.  Device
+    timed (CUDA events on the launching stream, which waits for NCCL's stream), max over ranks, median of 50."""
+    import torch
+    import torch.distributed as dist
+
+    from kd_6d_pose_adlp_b200.dist import GradBucket, global_mean_loss
+
+    out = {"backend": dist.get_backend(), "op": "all_reduce AVG, in place on the flat gradient bucket (zero copies)",
+           "timing": "CUDA events, 20 warm-up + 50 timed, median, max over ranks"}
+
+    def time_call(fn, iters=50, warm=20):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        barrier()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        return max_over_ranks(statistics.median(ts))
+
+    buckets = {}
+    for name, n in (("darknet_tiny_h", 2304468), ("darknet_tiny", 8486076)):
+        prm = torch.nn.Parameter(torch.zeros(n, device=dev))
+        bucket = GradBucket([prm])
+        bucket.flat.fill_(float(rank + 1))
+        us = time_call(lambda b=bucket: b.allreduce(average=True))
+        nbytes = n * 4
+        out[name] = {"elements": n, "bytes": nbytes, "us": us, "alg_GBps": nbytes / us / 1e3,
+                     "bus_GBps": 2.0 * (world - 1) / world * nbytes / us / 1e3}
+        buckets[name] = bucket
+    loss_sum = torch.ones((), device=dev)
+    out["global_mean_loss_us"] = time_call(lambda: global_mean_loss(loss_sum, 60))
+
+    # the loss kernel of the headline workload with the student-gradient all-reduce of the PREVIOUS step in flight
+    # (issued first: NCCL's stream then runs beside the kernel's stream; both are waited for before the stop event)
+    bucket = buckets["darknet_tiny_h"]
+
+    def overlapped():
+        work = bucket.allreduce(average=True, async_op=True)
+        bench.step()
+        if work is not None:
+            work.wait()
+
+    def serial():
+        bucket.allreduce(average=True)
+        bench.step()
+
+    out["step_with_allreduce"] = {
+        "workload": "ape_b64 + darknet_tiny_h bucket", "overlapped_us": time_call(overlapped), "serial_us": time_call(serial),
+        "kernel_only_us": time_call(bench.step),
+        "note": "no L2 flush between these launches (steady-state training step); the all-reduce, not the 2x-us loss "
+                "kernel, bounds an ape-shaped data-parallel step"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -491,23 +554,36 @@ def main():
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
 
-    if rank == 0 and world == 1 and not args.no_dense and args.workload != "dense_b32":
-        # secondary leg: the roofline-relevant dense configuration (BASELINE.json configs[2], variant 3b)
-        db = make_batch("dense_b32", 0)
+    if not args.no_dense and args.workload != "dense_b32":
+        # secondary leg on EVERY rank: the roofline-relevant dense configuration (BASELINE.json configs[2], variant 3b:
+        # "batch 256 sharded over 8 x B200" is exactly this leg at N = 8 -- 32 images per GPU).  Own clock sampler,
+        # device-timed, max over ranks; same L2 flush / restore protocol as the main leg.
+        d_steps = max(min(args.steps, 20), 3)
+        db = make_batch("dense_b32", rank)
         dbench = DeviceBench(db, dev)
-        d_total, d_per, d_launch = dbench.timed(3, 3, lambda: None)
-        d_ms = d_total / 3
+        d_sampler = ClockSampler(local_rank)
+        d_sampler.start()
+        d_total, d_per, d_launch = dbench.timed(d_steps, 3, barrier)
+        d_clocks = d_sampler.result()
+        d_ms = max_over_ranks(d_total) / d_steps
         d_fl, d_ex, d_by = algorithmic_work(db, dbench.nits.cpu().numpy())
+        d_kernel = kernel_name(dbench.max_n, dbench.max_m, d_launch // d_steps)
         line["dense"] = {
-            "workload": "dense_b32", "value": len(db["pos_per_img"]) / (d_ms * 1e-3), "unit": UNIT, "ms_per_step": d_ms,
-            "roofline": {"bound": "fp32", "kernel": kernel_name(dbench.max_n, dbench.max_m, d_launch // 3), "achieved": d_fl / (d_ms * 1e-3) / 1e12,
+            "workload": "dense_b32", "desc": WORKLOADS["dense_b32"]["desc"], "n_gpus": world, "steps": d_steps, "warmup": 3,
+            "value": len(db["pos_per_img"]) * world / (d_ms * 1e-3), "unit": UNIT, "ms_per_step": d_ms, "scaling": "weak",
+            "clocks": d_clocks,
+            "roofline": {"bound": "fp32", "kernel": d_kernel, "achieved": d_fl / (d_ms * 1e-3) / 1e12,
                          "peak": fp32_peak, "unit": "TFLOP/s", "frac": d_fl / (d_ms * 1e-3) / 1e12 / fp32_peak,
+                         "per": "GPU (rank 0's algorithmic FLOPs over the max-over-ranks step time)",
                          "sfu_exp_per_s": d_ex / (d_ms * 1e-3),
-                         "traffic": ncu_traffic_bytes(kernel_name(dbench.max_n, dbench.max_m, d_launch // 3), "dense_b32"),
+                         "traffic": ncu_traffic_bytes(d_kernel, "dense_b32"),
                          "algorithmic_bytes_per_step": d_by,
                          "hbm_gbs": d_by / (d_ms * 1e-3) / 1e9},
         }
         del dbench
+
+    if world > 1:
+        line["allreduce"] = allreduce_leg(dev, bench, barrier, max_over_ranks, world, rank)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = batch if WORKLOADS[args.workload]["dense"] is None else make_batch(args.workload, 0, nimg=1)

@@ -45,6 +45,18 @@ __device__ __forceinline__ bool is_hi_round(int r, int nrounds, float eps, float
   return r >= nrounds - KDOT_HI_ROUNDS && eps * 256.0f < eps0;
 }
 
+// Magnitude test that goes with is_hi_round: an fp32 soft-min argument carries an error of ~2^-24 max(|h_j|, |coef d^2|),
+// and an error made k rounds before the last one reaches the final h amplified by about 2^(k-1) (eps shrinks by
+// scaling^-p per round, the averaged update halves; fitted on the fp64 oracle).  Pairs whose
+// offsets stay below  kHiMagnitude * 2^(k+1)  are accurate enough in fp32:  hi iff  max|h| * hi_mag_factor(k) > 1.
+#ifndef KDOT_HI_MAGNITUDE
+#define KDOT_HI_MAGNITUDE 64.0f
+#endif
+constexpr float kHiMagnitude = KDOT_HI_MAGNITUDE;
+__device__ __forceinline__ float hi_mag_factor(int r, int nrounds) {
+  return exp2f(-(float)(nrounds - r)) / kHiMagnitude;  // k = nrounds - 1 - r rounds follow this one
+}
+
 // float64 -> fp32 of a soft-min argument difference without the XU pipe (F2F.F32.F64 shares it with MUFU.EX2 at 16
 // lanes/clk/SM): a 64-bit integer add of half an fp32 ulp (round to nearest, ties away) and three integer-pipe
 // operations that re-pack sign, exponent and the top 23 mantissa bits.  Valid for 2^-126 <= |u| < 2^127; smaller |u|

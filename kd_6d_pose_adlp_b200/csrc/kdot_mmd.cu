@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(kMmdThreads) kdot_mmd_kernel(MmdParams p) {
       const float* rbase = stu ? b.xs : b.xt;
       const float* rw = stu ? b.ws : b.wt;
       float xi[kMmdMaxD];
-      for (int d = 0; d < D; ++d) xi[d] = rbase[(size_t)D * gi + d] * inv_blur;
+      // scaled coordinates are formed by an explicit (non-contracted) multiply on both sides of every difference: an FMA
+      // xi - x_k * inv_blur would leave the rounding residual of x_i * inv_blur on the diagonal (k == i), and the Gaussian's
+      // -1/blur^2 turns that into a spurious 1e-4 gradient
+      for (int d = 0; d < D; ++d) xi[d] = __fmul_rn(rbase[(size_t)D * gi + d], inv_blur);
       const float wi = rw ? rw[gi] : __fdiv_rn(1.0f, (float)(stu ? N : M));
       float same = 0.f, cross = 0.f;  // (K alpha)_i over the own cloud, (K beta)_i over the other cloud
       float gs[kMmdMaxD], gc[kMmdMaxD];
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(kMmdThreads) kdot_mmd_kernel(MmdParams p) {
         for (int k = 0; k < cnt; ++k) {
           const long long gk = (long long)(c0 + k) * sc + (long long)slot * ss;
           float q = 0.f, df[kMmdMaxD];
-          for (int d = 0; d < D; ++d) { df[d] = xi[d] - rbase[(size_t)D * gk + d] * inv_blur; q = fmaf(df[d], df[d], q); }
+          for (int d = 0; d < D; ++d) { df[d] = __fsub_rn(xi[d], __fmul_rn(rbase[(size_t)D * gk + d], inv_blur)); q = fmaf(df[d], df[d], q); }
           const float wk = rw ? __ldg(rw + gk) : __fdiv_rn(1.0f, (float)cnt);
           float g;
           const float kv = mmd_kernel(p.kind, q, inv_blur, g);
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(kMmdThreads) kdot_mmd_kernel(MmdParams p) {
         for (int j = 0; j < M; ++j) {
           const long long gj = (long long)(m0 + j) * b.s_cell_m + (long long)slot * b.s_slot_m;
           float q = 0.f, df[kMmdMaxD];
-          for (int d = 0; d < D; ++d) { df[d] = xi[d] - b.xt[(size_t)D * gj + d] * inv_blur; q = fmaf(df[d], df[d], q); }
+          for (int d = 0; d < D; ++d) { df[d] = __fsub_rn(xi[d], __fmul_rn(b.xt[(size_t)D * gj + d], inv_blur)); q = fmaf(df[d], df[d], q); }
           const float wj = b.wt ? __ldg(b.wt + gj) : __fdiv_rn(1.0f, (float)M);
           float g;
           const float kv = mmd_kernel(p.kind, q, inv_blur, g);

@@ -117,8 +117,19 @@ __device__ __forceinline__ void fast_max(const float* __restrict__ cx, const flo
 template <int CH, bool GRAD>
 __device__ __forceinline__ RoundOut<CH, GRAD> hi_round(const double* __restrict__ d2s, const double* __restrict__ hd,
                                                        const float* __restrict__ cx, const float* __restrict__ cy,
-                                                       int nchx, float pxf, float pyf, double coef, float mX, float mY) {
-  const double refX = (double)mX + 2.0, refY = (double)mY + 2.0;
+                                                       int nchx, float pxf, float pyf, double coef, float mX, float mY,
+                                                       float hmag) {
+  double refX = (double)mX + 2.0, refY = (double)mY + 2.0;
+  if ((hmag + fabsf(mX) + fabsf(mY)) * 9.5e-7f > 1.0f) {
+    // offsets beyond ~1e6 log2-units (un-normalised pixel coordinates at blur = 1e-3): the fp32 estimate of the row
+    // maximum is no longer good to +-2, take the maxima in float64 (rare, slow: fmax on doubles)
+    double mx = -1.0e300, my = -1.0e300;
+    for (int j = 0; j < 4 * CH; ++j) {
+      const double t = fma(coef, d2s[j * 32], hd[j]);
+      if (j < 4 * nchx) mx = fmax(mx, t); else my = fmax(my, t);
+    }
+    refX = mx + 2.0; refY = my + 2.0;
+  }
   float sX = 0.f, sY = 0.f, gXx = 0.f, gXy = 0.f, gYx = 0.f, gYy = 0.f;
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
@@ -169,6 +180,7 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
   const int lane = threadIdx.x & 31;
   const float eps0 = (float)is.eps0;
   double potS = 0.0, potC = 0.0;
+  float hmag = 0.f;  // max |h| over this slot's columns, as published for the current round (hi_mag_factor test)
   int cur = 0;
   for (int r = 0; r < nrounds - 1; ++r) {
     if (r >= 32 && (r & 31) == 0)  // schedules longer than 32 rounds: next block of constants
@@ -179,7 +191,7 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
     const float coef = __shfl_sync(0xffffffffu, mine.coef, r & 31);
     const float eps = __shfl_sync(0xffffffffu, mine.eps, r & 31);
     const float* hp = c.hb + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
-    if (!is_hi_round(r, nrounds, eps, eps0)) {
+    if (!(is_hi_round(r, nrounds, eps, eps0) && hmag * hi_mag_factor(r, nrounds) > 1.0f)) {
       const RoundOut<CH, false> o = fast_round<CH, false>(c.cx, c.cy, hp, c.nchx, c.px, c.py, coef);
       lseX = o.lseX; lseY = o.lseY;
     } else {
@@ -187,15 +199,17 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
       const double* hpd = c.hbd + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
       float mX, mY;
       fast_max<CH>(c.cx, c.cy, hp, c.nchx, c.px, c.py, coef, mX, mY);
-      const RoundOut<CH, false> o = hi_round<CH, false>(c.d2s, hpd, c.cx, c.cy, c.nchx, c.px, c.py, coefd, mX, mY);
+      const RoundOut<CH, false> o = hi_round<CH, false>(c.d2s, hpd, c.cx, c.cy, c.nchx, c.px, c.py, coefd, mX, mY, hmag);
       lseX = o.lseX; lseY = o.lseY;
     }
     const double nS = scaled * (c.isx ? lseX : lseY);
     const double nC = scaled * (c.isx ? lseY : lseX);
     potS = r == 0 ? nS : 0.5 * (potS + nS);
     potC = r == 0 ? nC : 0.5 * (potC + nC);
+    hmag = 0.f;
     if (c.act) {
       const double hS = fma(potS, hmuld, c.lw2d), hC = fma(potC, hmuld, c.lw2d);
+      hmag = fmaxf(fabsf((float)hS), fabsf((float)hC));
       float* hn = c.hb + (cur ^ 1) * (2 * kFastMaxCols);
       double* hnd = c.hbd + (cur ^ 1) * (2 * kFastMaxCols);
       hn[c.col] = (float)(c.isx ? hS : hC);                  // view 0: what student rows read for this column
@@ -204,6 +218,7 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
       hnd[kFastMaxCols + c.col] = c.isx ? hC : hS;
     }
     __syncwarp();
+    hmag = warp_max(hmag);
     cur ^= 1;
   }
   const int r = nrounds - 1;
@@ -219,7 +234,7 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
   double lseX, lseY;
   float sX, sY, gXx, gXy, gYx, gYy;
   const float* hp = c.hb + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
-  if (!is_hi_round(r, nrounds, rc_last.eps, eps0)) {
+  if (!(is_hi_round(r, nrounds, rc_last.eps, eps0) && hmag * hi_mag_factor(r, nrounds) > 1.0f)) {
     const RoundOut<CH, true> o = fast_round<CH, true>(c.cx, c.cy, hp, c.nchx, c.px, c.py, rc_last.coef);
     lseX = o.lseX; lseY = o.lseY; sX = o.sX; sY = o.sY;
     gXx = o.gXx; gXy = o.gXy; gYx = o.gYx; gYy = o.gYy;
@@ -227,7 +242,7 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
     const double* hpd = c.hbd + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
     float mX, mY;
     fast_max<CH>(c.cx, c.cy, hp, c.nchx, c.px, c.py, rc_last.coef, mX, mY);
-    const RoundOut<CH, true> o = hi_round<CH, true>(c.d2s, hpd, c.cx, c.cy, c.nchx, c.px, c.py, rc_last.coefd, mX, mY);
+    const RoundOut<CH, true> o = hi_round<CH, true>(c.d2s, hpd, c.cx, c.cy, c.nchx, c.px, c.py, rc_last.coefd, mX, mY, hmag);
     lseX = o.lseX; lseY = o.lseY; sX = o.sX; sY = o.sY;
     gXx = o.gXx; gXy = o.gXy; gYx = o.gYx; gYy = o.gYy;
   }

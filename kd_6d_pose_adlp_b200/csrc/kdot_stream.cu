@@ -56,6 +56,8 @@ struct StreamParams {
   float* hmax;   // [nprob][2 buffers][2][strideP/32]  max of h over the tile, maintained by the units that write h
   unsigned short* jb;  // [nprob][2][strideP]  (value = sub-tile index = column / 32)          per row and column set (own, cross): first column of the chunk that held
                  //                              the row's running max in the previous round (seeds the next sweep)
+  double* pref;       // [nprob][3][4]            reference potentials the published h is centred on (see stream_unit), slot r % 3
+  unsigned int* hmag; // [nprob][3]               max |h| (fp32 bits) of the offsets consumed in round r: slot r % 3; gates the float64 path
   unsigned int* ctr;  // [KDOT_MAX_ROUNDS]       first 8 bytes: 64-bit head of the global unit FIFO
   unsigned int* done; // [nprob]                 finished units per problem (all rounds)
 };
@@ -245,83 +247,181 @@ struct TileSkip {
 // What stays fp32 adds up to < 32 * kSigThr per row with ~1e-3 relative error each: < 1e-6 of the sum.
 // The gradient round evaluates every sub-tile it does not skip this way (its weights enter d/dx directly).
 constexpr float kSigThr = 1.0f / 16384.0f;
+// Stream-kernel value of kHiMagnitude (kdot_common.cuh).  Clouds of several hundred points and more: the max-norm of the
+// d/dx error is set by a few ill-conditioned cells (near-ties between neighbours) that react to the 2^-22 error of
+// ex2.approx itself -- 2e-5..1.7e-4 with or without float64 arguments (tools/accuracy_report.py on 16 streaming cases:
+// mean 4e-5 vs 6e-5) -- while the screened float64 sub-tiles cost dense_b32 12 %.  They are therefore reserved for
+// problems whose CENTRED offsets exceed 8192 log2-units in the last round (fp32 argument error > 5e-4: wide, sparse clouds).
+constexpr float kStreamHiMagnitude = 4096.0f;
 
 struct HiArgs {
   const float* chlo;  // fp32 tail of h for the column set (same indexing as ch)
   double* hsm;        // per-warp staging: [D + 1][32] float64
   double coefd;
+  float mag_fac;      // hi_mag_factor of this round: a sub-tile needs float64 arguments iff max|h| * mag_fac > 1
+  long long* dbg;     // profiling aid (kdot_debug_set_clock_buffer): [5] screened, [6] float64 sub-tiles, [7] gradient-round float64 sub-tiles
 };
+
+// Staging of one sub-tile for the float64 evaluation.  The argument is evaluated in the EXPANDED form
+//   u_ij = h_j + coef |x_j|^2  +  coef |p_i|^2 - ref_i  -  2 coef <x_j, p_i>        (exact enough in float64: 1e-10)
+// so a pair costs D + 1 DP operations instead of 2 D + 2: the column part G_j = h_j + coef |x_j|^2 is staged, the row
+// part K_i and the vector -2 coef p_i are formed once per sub-tile.  Everything is scaled by kRnd = 1 + 2^-25, which turns
+// the truncation of f64_to_f32_trunc_nz-style re-packing into (nearly) round-to-nearest at no cost per pair.
+constexpr double kRnd = 1.0 + 1.0 / 33554432.0;
 
 template <int D>
 __device__ __forceinline__ void stage_hi(double* hsm, const float* tb, int T, int sb, int lane, const float* chlo_sub,
-                                         bool valid) {
+                                         bool valid, double coefd) {
   __syncwarp();  // previous readers of the staging buffer are done
+  double xx = 0.0;
 #pragma unroll
-  for (int d = 0; d < D; ++d) hsm[d * 32 + lane] = (double)tb[d * T + sb + lane];
+  for (int d = 0; d < D; ++d) {
+    const double x = (double)tb[d * T + sb + lane];
+    hsm[d * 32 + lane] = x;
+    xx = fma(x, x, xx);
+  }
   const float lo = valid ? __ldcg(chlo_sub + lane) : 0.f;
-  hsm[D * 32 + lane] = (double)tb[D * T + sb + lane] + (double)lo;
+  const double h = (double)tb[D * T + sb + lane] + (double)lo;
+  hsm[D * 32 + lane] = fma(coefd, xx, h) * kRnd;
   __syncwarp();
 }
 
-// The R rows of this lane against the ncol (multiple of 4, <= 32) staged columns; same lazily re-based running sums as
-// stream_chunk (mref stays an fp32 number: it is exactly representable in float64).
+// max |h| over the real columns of a staged 32-column sub-tile (pads carry -big)
+template <int D>
+__device__ __forceinline__ float subtile_hmag(const float* tb, int T, int sb, int n, int lane) {
+  float v = 0.f;
+  if (sb + lane < n) {
+    const float h = tb[D * T + sb + lane];
+    v = h > -1.0e29f ? fabsf(h) : 0.f;
+  }
+  return warp_max(v);
+}
+
+// float64 -> fp32 re-packing of an argument difference: integer pipe (exact 0 / tiny |u| -> 0), see kdot_common.cuh
+__device__ __forceinline__ float hi_pack(double u) {
+  const unsigned int hi = (unsigned int)__double2hiint(u), lo = (unsigned int)__double2loint(u);
+  const unsigned int packed = __funnelshift_l(lo, hi, 3) ^ 0x40000000u;
+  const unsigned int bits = (packed & 0x7fffffffu) | (hi & 0x80000000u);
+  return ((hi & 0x7ff00000u) < (897u << 20)) ? 0.f : __uint_as_float(bits);
+}
+
+// The R rows of this lane against the ncol (multiple of 4, <= 32) columns of one sub-tile in float64; same lazily
+// re-based running sums as stream_chunk (the reference stays an fp32 number: exactly representable in float64).  Three of
+// four conversions go through the integer pipe, the fourth through F2F on the XU pipe (which also serves the ex2).
+// Deliberately NOT inlined, state passed and returned by value: the float64 code needs ~2x the registers of the fp32
+// sweep, and inlined it cost the fp32 hot loop of the same instantiation 10 % (measured on dense_b32) although it runs
+// for a few per cent of the sub-tiles only.
 template <int D, int R, bool GRAD>
-__device__ __forceinline__ void stream_subtile_hi(URow<D, R, GRAD> (&st)[R], const double* __restrict__ hsm,
-                                                  const float* __restrict__ tb, int T, int sb, int ncol, double coefd,
-                                                  float inv_ncoef, float big) {
+struct HiIO {
+  float nx[R][D];   // -p_i
+  float mref[R];    // reference exponent (in / out)
+  float2 s[R];      // running sums (in / out)
+  float2 g[GRAD ? R * D : 1];  // gradient accumulators (in / out)
+  float sc[R];      // out: product of the re-basing factors applied to s (1 when the reference did not move)
+};
+
+template <int D, int R, bool GRAD>
+__device__ __noinline__ HiIO<D, R, GRAD> subtile_hi(HiIO<D, R, GRAD> io, double* hsm, const float* tb, int T, int sb,
+                                                    int ncol, int lane, const float* chlo_sub, bool valid, double coefd,
+                                                    float big) {
+  stage_hi<D>(hsm, tb, T, sb, lane, chlo_sub, valid, coefd);
+  double ax[R][D], K[R];
+  const double c2 = -2.0 * coefd * kRnd;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    double pp = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double pd = -(double)io.nx[k][d];
+      ax[k][d] = c2 * pd;
+      pp = fma(pd, pd, pp);
+    }
+    K[k] = fma(coefd, pp, -(double)io.mref[k]) * kRnd;
+    io.sc[k] = 1.0f;
+  }
 #pragma unroll 1
   for (int j = 0; j < ncol; j += 4) {
-    double q[R][4];
+    const double2 G0 = *reinterpret_cast<const double2*>(hsm + D * 32 + j);
+    const double2 G1 = *reinterpret_cast<const double2*>(hsm + D * 32 + j + 2);
+    double u[R][4];
 #pragma unroll
-    for (int k = 0; k < R; ++k) { q[k][0] = 0.0; q[k][1] = 0.0; q[k][2] = 0.0; q[k][3] = 0.0; }
+    for (int k = 0; k < R; ++k) { u[k][0] = G0.x + K[k]; u[k][1] = G0.y + K[k]; u[k][2] = G1.x + K[k]; u[k][3] = G1.y + K[k]; }
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       const double2 A = *reinterpret_cast<const double2*>(hsm + d * 32 + j);
       const double2 Bv = *reinterpret_cast<const double2*>(hsm + d * 32 + j + 2);
 #pragma unroll
       for (int k = 0; k < R; ++k) {
-        const double nd = (double)st[k].nx[d];  // -p_i (loop invariant)
-        const double a0 = A.x + nd, a1 = A.y + nd, a2 = Bv.x + nd, a3 = Bv.y + nd;
-        q[k][0] = fma(a0, a0, q[k][0]); q[k][1] = fma(a1, a1, q[k][1]);
-        q[k][2] = fma(a2, a2, q[k][2]); q[k][3] = fma(a3, a3, q[k][3]);
+        u[k][0] = fma(A.x, ax[k][d], u[k][0]); u[k][1] = fma(A.y, ax[k][d], u[k][1]);
+        u[k][2] = fma(Bv.x, ax[k][d], u[k][2]); u[k][3] = fma(Bv.y, ax[k][d], u[k][3]);
       }
     }
-    const double2 H0 = *reinterpret_cast<const double2*>(hsm + D * 32 + j);
-    const double2 H1 = *reinterpret_cast<const double2*>(hsm + D * 32 + j + 2);
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      const double t0 = fma(coefd, q[k][0], H0.x), t1 = fma(coefd, q[k][1], H0.y);
-      const double t2 = fma(coefd, q[k][2], H1.x), t3 = fma(coefd, q[k][3], H1.y);
-      double mr = (double)st[k].mref;
-      float p0 = ex2_approx(f64_to_f32_trunc(t0 - mr)), p1 = ex2_approx(f64_to_f32_trunc(t1 - mr));
-      float p2 = ex2_approx(f64_to_f32_trunc(t2 - mr)), p3 = ex2_approx(f64_to_f32_trunc(t3 - mr));
+      float p0 = ex2_approx(hi_pack(u[k][0])), p1 = ex2_approx(hi_pack(u[k][1]));
+      float p2 = ex2_approx(hi_pack(u[k][2])), p3 = ex2_approx((float)u[k][3]);
       if (!((p0 + p1) + (p2 + p3) <= big)) {  // cold: re-base on the max of this chunk
-        const float vm = (float)fmax(fmax(t0, t1), fmax(t2, t3));
-        const float sc = ex2_approx(st[k].mref - vm);  // 0 for the first chunk (mref = -big)
-        st[k].s.x *= sc; st[k].s.y *= sc;
+        const float um = (float)fmax(fmax(u[k][0], u[k][1]), fmax(u[k][2], u[k][3]));  // relative to the old reference
+        const float vm = io.mref[k] + um;                                                  // any fp32 number near the max will do
+        const float sc = ex2_approx(io.mref[k] - vm);  // 0 for the first chunk (mref = -big)
+        const double shift = ((double)vm - (double)io.mref[k]) * kRnd;  // exact difference of two fp32 numbers
+        io.s[k].x *= sc; io.s[k].y *= sc;
         if (GRAD) {
 #pragma unroll
-          for (int d = 0; d < D; ++d) { st[k].g[d].x *= sc; st[k].g[d].y *= sc; }
+          for (int d = 0; d < D; ++d) { io.g[k * D + d].x *= sc; io.g[k * D + d].y *= sc; }
         }
-        st[k].mref = vm;
-        st[k].gbest *= sc;
-        st[k].s0 *= sc;
-        const float mu = vm * inv_ncoef;
-        st[k].mu = make_float2(mu, mu);
-        mr = (double)vm;
-        p0 = ex2_approx(f64_to_f32_trunc(t0 - mr)); p1 = ex2_approx(f64_to_f32_trunc(t1 - mr));
-        p2 = ex2_approx(f64_to_f32_trunc(t2 - mr)); p3 = ex2_approx(f64_to_f32_trunc(t3 - mr));
+        io.mref[k] = vm;
+        io.sc[k] *= sc;
+        K[k] -= shift;
+        p0 = ex2_approx(hi_pack(u[k][0] - shift)); p1 = ex2_approx(hi_pack(u[k][1] - shift));
+        p2 = ex2_approx(hi_pack(u[k][2] - shift)); p3 = ex2_approx((float)(u[k][3] - shift));
       }
-      st[k].s.x += p0 + p2; st[k].s.y += p1 + p3;
+      io.s[k].x += p0 + p2; io.s[k].y += p1 + p3;
       if (GRAD) {  // weights from the float64 argument, coordinate differences in fp32 (exact enough: they are O(cloud size))
 #pragma unroll
         for (int d = 0; d < D; ++d) {
           const float4 X = *reinterpret_cast<const float4*>(tb + d * T + sb + j);
-          const float nd = st[k].nx[d];
-          st[k].g[d].x = fmaf(p0, X.x + nd, fmaf(p2, X.z + nd, st[k].g[d].x));
-          st[k].g[d].y = fmaf(p1, X.y + nd, fmaf(p3, X.w + nd, st[k].g[d].y));
+          const float nd = io.nx[k][d];
+          io.g[k * D + d].x = fmaf(p0, X.x + nd, fmaf(p2, X.z + nd, io.g[k * D + d].x));
+          io.g[k * D + d].y = fmaf(p1, X.y + nd, fmaf(p3, X.w + nd, io.g[k * D + d].y));
         }
       }
+    }
+  }
+  return io;
+}
+
+// glue: URow state <-> HiIO
+template <int D, int R, bool GRAD>
+__device__ __forceinline__ void stream_subtile_hi(URow<D, R, GRAD> (&st)[R], double* hsm, const float* tb, int T, int sb,
+                                                  int ncol, int lane, const float* chlo_sub, bool valid, double coefd,
+                                                  float inv_ncoef, float big) {
+  HiIO<D, R, GRAD> io;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) io.nx[k][d] = st[k].nx[d];
+    io.mref[k] = st[k].mref;
+    io.s[k] = st[k].s;
+    if (GRAD) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) io.g[k * D + d] = st[k].g[d];
+    }
+  }
+  io = subtile_hi<D, R, GRAD>(io, hsm, tb, T, sb, ncol, lane, chlo_sub, valid, coefd, big);
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    st[k].s = io.s[k];
+    if (GRAD) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) st[k].g[d] = io.g[k * D + d];
+    }
+    if (io.mref[k] != st[k].mref) {
+      st[k].mref = io.mref[k];
+      st[k].gbest *= io.sc[k];
+      st[k].s0 *= io.sc[k];
+      const float mu = io.mref[k] * inv_ncoef;
+      st[k].mu = make_float2(mu, mu);
     }
   }
 }
@@ -387,9 +487,41 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
         for (int k = 0; k < R; ++k) st[k].s0 = st[k].s.x + st[k].s.y;
       }
       const int je = min(sb + 32, n);
-      if (HI && GRAD) {  // gradient round: float64 arguments for every evaluated sub-tile
-        stage_hi<D>(ha.hsm, tb, T, sb, lane, ha.chlo + t * T + sb, sb + lane < n);
-        stream_subtile_hi<D, R, GRAD>(st, ha.hsm, tb, T, sb, je - sb, ha.coefd, inv_ncoef, big);
+      bool grad_hi = false;
+#ifdef KDOT_NO_GRAD_HI
+      constexpr bool kGradHi = false;
+#else
+      constexpr bool kGradHi = true;
+#endif
+      if (kGradHi && HI && GRAD && subtile_hmag<D>(tb, T, sb, n, lane) * ha.mag_fac > 1.0f) {
+        // gradient round: float64 arguments for the sub-tiles that carry a visible share of a row's weights.  Screen with
+        // a sums-only fp32 pass on copies (no state is touched); an overflow counts as "visible".
+        URow<D, R, false> tmp[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) tmp[k].nx[d] = st[k].nx[d];
+          tmp[k].mref = st[k].mref; tmp[k].mu = st[k].mu; tmp[k].s = make_float2(0.f, 0.f);
+        }
+#pragma unroll 2
+        for (int j = sb; j < je; j += 4) {
+          float4 X[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) X[d] = *reinterpret_cast<const float4*>(tb + d * T + j);
+          const float4 H = *reinterpret_cast<const float4*>(tb + D * T + j);
+          stream_chunk_spec<D, R, false>(tmp, X, H, coef2);
+        }
+        bool sig = false;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const float gain = tmp[k].s.x + tmp[k].s.y;
+          sig |= !(gain <= kSigThr * fmaxf(st[k].s0 + gain, 1.0f));
+        }
+        grad_hi = __any_sync(0xffffffffu, sig);
+        if (ha.dbg && lane == 0) { atomicAdd((unsigned long long*)ha.dbg + 5, 1ull); if (grad_hi) atomicAdd((unsigned long long*)ha.dbg + 7, 1ull); }
+      }
+      if (HI && GRAD && grad_hi) {
+        stream_subtile_hi<D, R, GRAD>(st, ha.hsm, tb, T, sb, je - sb, lane, ha.chlo + t * T + sb, sb + lane < n, ha.coefd, inv_ncoef, big);
       } else {
         bool redo = true;
         if (!GRAD && !P1 && D <= 2) {  // speculate: whole sub-tile without overflow tests, one check at the end (larger D: registers)
@@ -422,18 +554,23 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
             stream_chunk<D, R, GRAD, FOLD, P1>(st, X, H, coef2, inv_ncoef, big);
           }
         }
-        if (HI) {  // screen: does this sub-tile carry a visible share of any row's sum?
+#ifdef KDOT_NO_POT_HI
+        constexpr bool kPotHi = false;
+#else
+        constexpr bool kPotHi = true;
+#endif
+        if (kPotHi && HI && !GRAD) {  // screen: does this sub-tile carry a visible share of any row's sum?
           bool sig = false;
 #pragma unroll
           for (int k = 0; k < R; ++k) {
             const float sk = st[k].s.x + st[k].s.y;
             sig |= (sk - st[k].s0) > kSigThr * fmaxf(sk, 1.0f);
           }
-          if (__any_sync(0xffffffffu, sig)) {
+          if (__any_sync(0xffffffffu, sig) && subtile_hmag<D>(tb, T, sb, n, lane) * ha.mag_fac > 1.0f) {
+            if (ha.dbg && lane == 0) atomicAdd((unsigned long long*)ha.dbg + 6, 1ull);
 #pragma unroll
             for (int k = 0; k < R; ++k) st[k].s = make_float2(st[k].s0, 0.f);  // drop the fp32 contribution (s0 follows re-basing)
-            stage_hi<D>(ha.hsm, tb, T, sb, lane, ha.chlo + t * T + sb, sb + lane < n);
-            stream_subtile_hi<D, R, GRAD>(st, ha.hsm, tb, T, sb, je - sb, ha.coefd, inv_ncoef, big);
+            stream_subtile_hi<D, R, GRAD>(st, ha.hsm, tb, T, sb, je - sb, lane, ha.chlo + t * T + sb, sb + lane < n, ha.coefd, inv_ncoef, big);
           }
         }
       }
@@ -528,7 +665,21 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   const RoundConst rc = b.sched[(size_t)img * KDOT_MAX_ROUNDS + r];
   const float eps0 = b.sched[(size_t)img * KDOT_MAX_ROUNDS].eps;
   const bool warm = !P1 && rc.eps * 256.0f >= eps0;   // reference exponent folded into the distance chain (one op less per pair)
-  const bool hi = !P1 && is_hi_round(r, nrounds, rc.eps, eps0);
+  // float64 pair arguments only for problems whose offsets are large enough for fp32 to hurt (kStreamHiMagnitude): the
+  // screened float64 sub-tiles cost the dense configurations ~12 % for no measurable gain in accuracy (their |h| stays
+  // in the hundreds), while sparse / wide clouds (|h| ~ 1e4) need them
+  // Centred offsets.  Unbalanced OT with unequal total masses puts a common term of order rho * log(mass ratio) / eps
+  // (1e4 log2-units at eps = 1e-6) into every potential of a cloud; it cancels in h_j - max_j, but an fp32 head of h
+  // would spend its mantissa on it.  The h of every (type S/C, cloud X/Y) set is therefore published relative to
+  // c = pot(row 0 of that set, two rounds earlier) * hmul -- a value every unit of the round can read without a race --
+  // and the same c is added back to the log-sum-exp in float64.  pref[slot q % 3] holds the raw potentials for the h
+  // consumed in round q; it is written in round q - 2 by the unit that owns row 0.
+  double* pref = p.pref + (size_t)prob * 12;
+  const double hmul_prev = r > 0 ? b.sched[(size_t)img * KDOT_MAX_ROUNDS + r - 1].hmuld : 0.0;
+  unsigned int* hmag = p.hmag + (size_t)prob * 3;
+  const bool hi = !P1 && is_hi_round(r, nrounds, rc.eps, eps0) &&
+                  __uint_as_float(__ldcg(hmag + r % 3)) * hi_mag_factor(r, nrounds) * (kHiMagnitude / kStreamHiMagnitude) > 1.0f;
+  if (uu == 0 && lane == 0) hmag[(r + 2) % 3] = 0u;  // slot of round r + 2: last read in round r - 1, next written in round r + 1
   const double rho = b.rho;
   const float* pts = p.pts + (size_t)prob * D * strideP;
   const float* lw2 = p.lw2 + (size_t)prob * strideP;
@@ -553,6 +704,8 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   HiArgs ha{};
   ha.hsm = reinterpret_cast<double*>(wsm + 2 * (D + 1) * T);
   ha.coefd = rc.coefd;
+  ha.mag_fac = hi_mag_factor(r, nrounds) * (kHiMagnitude / kStreamHiMagnitude);
+  ha.dbg = b.dbg_clk;
 
   if (last && rows_x) {
     if (!own) return;  // the student's last round is done by the "own" unit for both column sets
@@ -576,7 +729,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
       else if (!warm) stream_rows<D, 1, true, false, P1, kSeed, kTSkip, false>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane, ts);
       else stream_rows<D, 1, true, false, P1, false, false, false>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane);
       const float sS = st[0].s.x + st[0].s.y;
-      const double S = rc.scaled * ((double)st[0].mref + lg2_sum_exact(sS));
+      const double S = rc.scaled * ((double)st[0].mref + lg2_sum_exact(sS) + __ldcg(pref + (r % 3) * 4 + 0) * hmul_prev);  // type S, cloud X
       float gS[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) gS[d] = (st[0].g[d].x + st[0].g[d].y) / sS;
@@ -592,7 +745,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
       else stream_rows<D, 1, true, false, P1, false, false, false>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane);
       if (!act) continue;
       const float sC = st[0].s.x + st[0].s.y;
-      const double C = rc.scaled * ((double)st[0].mref + lg2_sum_exact(sC));
+      const double C = rc.scaled * ((double)st[0].mref + lg2_sum_exact(sC) + __ldcg(pref + (r % 3) * 4 + 3) * hmul_prev);  // type C, cloud Y
       const RowFinal f = row_final(S, C, rho, rc.eps);
       const float lam = rho < 0.0 ? 1.f : (float)(1.0 / (1.0 + (double)rc.eps / rho));
       const float gfac = rho < 0.0 ? 1.f : (float)((rho + 0.5 * (double)rc.eps) / rho) * lam;
@@ -649,6 +802,8 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
     else stream_rows<D, R, false, false, P1, kSeed, kTSkip, false>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane, ts);
   }
   // new potentials / next round's h in float64; fp32 head + tail of h, per-tile maximum of the head (skip test)
+  const double c_in = __ldcg(pref + (r % 3) * 4 + (own ? 0 : 2) + (cols_x ? 0 : 1)) * hmul_prev;      // consumed h: its centre
+  const double p_out = last ? 0.0 : __ldcg(pref + ((r + 1) % 3) * 4 + (own ? 0 : 2) + (rows_x ? 0 : 1));  // published h: centred on this
   double hv[R];
 #pragma unroll
   for (int k = 0; k < R; ++k) {
@@ -658,17 +813,25 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
     // warm rounds fold the reference into the distance chain as mu = fl(mref / -coef): the sums are relative to
     // -coef * mu, which differs from mref by the rounding of mu (6e-8 |mref|: up to 1e-5) -- add back what was subtracted
     const double ref = warm ? -(double)rc.coef * (double)st[k].mu.x : (double)st[k].mref;
-    const double lse = ref + lg2_sum_exact(st[k].s.x + st[k].s.y);
+    const double lse = ref + lg2_sum_exact(st[k].s.x + st[k].s.y) + c_in;
     double* pot = own ? potS : potC;
     const double nv = rc.scaled * lse;
     const double pv = (r == 0 || last) ? nv : 0.5 * (__ldcg(pot + ridx[k]) + nv);
     pot[ridx[k]] = pv;
     if (!last) {
-      hv[k] = fma(pv, rc.hmuld, (double)__ldcg(lw2 + ridx[k]));
+      hv[k] = fma(pv - p_out, rc.hmuld, (double)__ldcg(lw2 + ridx[k]));
+      if (ridx[k] == rbase) pref[((r + 2) % 3) * 4 + (own ? 0 : 2) + (rows_x ? 0 : 1)] = pv;  // row 0 of this set: centre of the h consumed in round r + 2
       const float hh = (float)hv[k];
       (own ? hSn : hCn)[ridx[k]] = hh;
       (own ? lSn : lCn)[ridx[k]] = (float)(hv[k] - (double)hh);
     }
+  }
+  if (!last) {
+    float am = 0.f;
+#pragma unroll
+    for (int k = 0; k < R; ++k) am = fmaxf(am, ridx[k] >= 0 ? fabsf((float)hv[k]) : 0.f);
+    am = warp_max(am);
+    if (lane == 0) atomicMax(hmag + (r + 1) % 3, __float_as_uint(am));  // non-negative floats order like their bits
   }
   if (kTSkip && !last) {  // per-tile maximum of the h values this unit publishes (rows of pass k = one tile)
 #pragma unroll
@@ -775,7 +938,11 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
     __syncthreads();
   }
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < KDOT_MAX_ROUNDS; r += gridDim.x * blockDim.x) p.ctr[r] = 0u;
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nprob; q += gridDim.x * blockDim.x) p.done[q] = 0u;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nprob; q += gridDim.x * blockDim.x) {
+    p.done[q] = 0u;
+    p.hmag[3 * q] = 0u; p.hmag[3 * q + 1] = 0u; p.hmag[3 * q + 2] = 0u;
+    for (int a = 0; a < 12; ++a) p.pref[12 * (size_t)q + a] = 0.0;
+  }
   grid.sync();
 
   if (b.dbg_clk && blockIdx.x == 0 && threadIdx.x == 0) b.dbg_clk[1] = (long long)global_ns();
@@ -965,7 +1132,7 @@ __global__ void __launch_bounds__(kStreamThreads, (D <= 2 ? KDOT_STREAM_MINBLOCK
 
 struct StreamPlan {
   int strideP, nqMax, nbx, nby, upp, R;
-  size_t off_pts, off_lw, off_pot, off_h, off_hlo, off_perm, off_jb, off_tbox, off_hmax, off_ctr, off_done, off_sched, off_rounds, total;
+  size_t off_pts, off_lw, off_pot, off_h, off_hlo, off_perm, off_jb, off_tbox, off_hmax, off_hmag, off_pref, off_ctr, off_done, off_sched, off_rounds, total;
 };
 
 static int rows_per_lane(int D) { return D <= 2 ? KDOT_STREAM_R2 : (D <= 8 ? 2 : 1); }
@@ -991,6 +1158,8 @@ StreamPlan plan_stream(int nimg, int max_n, int max_m, int B, int D) {
   s.off_jb = o;     o = up(o + nprob * 2 * P * 2);
   s.off_tbox = o;   o = up(o + nprob * (P / 32) * 16);
   s.off_hmax = o;   o = up(o + nprob * 4 * (P / 32) * 4);
+  s.off_hmag = o;   o = up(o + nprob * 3 * 4);
+  s.off_pref = o;   o = up(o + nprob * 12 * 8);
   s.off_ctr = o;    o = up(o + (size_t)KDOT_MAX_ROUNDS * 4);
   s.off_done = o;   o = up(o + nprob * 4);
   s.off_sched = o;  o = up(o + (size_t)nimg * KDOT_MAX_ROUNDS * sizeof(RoundConst));
@@ -1045,6 +1214,8 @@ cudaError_t launch_stream(const SinkhornParams& prm, int D, int max_n, int max_m
   sp.jb = (unsigned short*)(base + pl.off_jb);
   sp.tbox = (float4*)(base + pl.off_tbox);
   sp.hmax = (float*)(base + pl.off_hmax);
+  sp.hmag = (unsigned int*)(base + pl.off_hmag);
+  sp.pref = (double*)(base + pl.off_pref);
   sp.ctr = (unsigned int*)(base + pl.off_ctr);
   sp.done = (unsigned int*)(base + pl.off_done);
   if (prm.sp.p == 1.0) return D == 2 ? launch_stream_t<2, KDOT_STREAM_R2, true>(sp, stream) : cudaErrorInvalidValue;

@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
   float* hC = hS + 2 * Pq;        // [2][Pq]
   const RoundConst* __restrict__ rcs = prm.sched + (size_t)img * KDOT_MAX_ROUNDS;  // L1/L2-resident, 1 load / round
   __shared__ unsigned int s_ctr[2];
+  __shared__ unsigned int s_hmag[3];  // max |h| (fp32 bits) of the values consumed in round r, slot r % 3 (hi_mag_factor test)
   __shared__ double s_part[kTiledThreads / 32];
 
   // ---- stage the cloud of this slot (already normalised by the prep kernel) ----
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
     hSd[q] = (double)l2; hCd[q] = (double)l2;
     hSd[Pq + q] = (double)l2; hCd[Pq + q] = (double)l2;
   }
-  if (threadIdx.x == 0) { s_ctr[0] = 0u; s_ctr[1] = 0u; }
+  if (threadIdx.x == 0) { s_ctr[0] = 0u; s_ctr[1] = 0u; s_hmag[0] = 0u; s_hmag[1] = 0u; s_hmag[2] = 0u; }
   __syncthreads();
 
   const int nbx = (N + kUnitRows - 1) / kUnitRows, nby = (M + kUnitRows - 1) / kUnitRows;
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
   int cur = 0;
   for (int r = 0; r < nrounds - 1; ++r) {
     const RoundConst rc = rcs[r];
-    const bool hi = is_hi_round(r, nrounds, rc.eps, rcs[0].eps);
+    const bool hi = is_hi_round(r, nrounds, rc.eps, rcs[0].eps) && __uint_as_float(s_hmag[r % 3]) * hi_mag_factor(r, nrounds) > 1.0f;
     const float* hSc = hS + cur * Pq;
     const float* hCc = hC + cur * Pq;
     float* hSn = hS + (cur ^ 1) * Pq;
@@ -423,6 +424,7 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
           lse[k] = sh.mref + lg2_sum_exact(sh.s.x + sh.s.y);
         }
       }
+      float hm = 0.f;
 #pragma unroll
       for (int k = 0; k < kRows; ++k) {
         if (ridx[k] < 0) continue;
@@ -433,9 +435,12 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
         const double hv = fma(pv, rc.hmuld, (double)lw2[ridx[k]]);
         (own ? hSn : hCn)[ridx[k]] = (float)hv;
         (own ? hSnd : hCnd)[ridx[k]] = hv;
+        hm = fmaxf(hm, fabsf((float)hv));
       }
+      hm = warp_max(hm);
+      if (lane == 0) atomicMax(&s_hmag[(r + 1) % 3], __float_as_uint(hm));  // non-negative floats order like their bits
     }
-    if (threadIdx.x == 0) s_ctr[(r & 1) ^ 1] = 0u;
+    if (threadIdx.x == 0) { s_ctr[(r & 1) ^ 1] = 0u; s_hmag[(r + 2) % 3] = 0u; }
     __syncthreads();
     cur ^= 1;
   }
@@ -444,7 +449,7 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
   {
     const int r = nrounds - 1;
     const RoundConst rc = rcs[r];
-    const bool hi = is_hi_round(r, nrounds, rc.eps, rcs[0].eps);
+    const bool hi = is_hi_round(r, nrounds, rc.eps, rcs[0].eps) && __uint_as_float(s_hmag[r % 3]) * hi_mag_factor(r, nrounds) > 1.0f;
     const float* hSc = hS + cur * Pq;
     const float* hCc = hC + cur * Pq;
     const double* hScd = hSd + cur * Pq;

@@ -26,7 +26,7 @@ def run_gpu(batch, blur=0.001, reach=0.5, scaling=0.5, normalize=True, weighted=
     return res
 
 
-def check(batch, **kw):
+def check(batch, tol=parity.TOL, **kw):
     g = run_gpu(batch, **kw)
     l32, gx32, gw32, xsn32, xtn32 = refs.ref32(batch, **kw)
     o64 = refs.ref64(batch, **kw)
@@ -39,7 +39,7 @@ def check(batch, **kw):
         np.testing.assert_array_equal(g["xt_norm"], xtn32)
     assert np.all(g["loss_per_img"][~keep] == 0)
     rows = [parity.report("loss_per_img", g["loss_per_img"], l32, o64["loss_per_img"]),
-            parity.report("grad_xs", g["grad_xs"], gx32, o64["grad_xs"])]
+            parity.report("grad_xs", g["grad_xs"], gx32, o64["grad_xs"], tol=tol)]
     if kw.get("weighted", True):
         rows.append(parity.report("grad_ws", g["grad_ws"], gw32, o64["grad_ws"]))
     print("\n" + parity.fmt(rows))
@@ -61,7 +61,7 @@ def test_balanced_and_unweighted():
     b = ot_batch(6, seed=11)
     check(b, reach=None)
     check(b, weighted=False)
-    check(b, normalize=False) if False else None
+    check(b, normalize=False)   # SamplesLoss called on already-normalised coordinates (seam B2)
 
 
 @pytest.mark.parametrize("scaling,blur", [(0.7, 0.001), (0.9, 0.01), (0.5, 0.05)])
@@ -78,8 +78,9 @@ def test_tiled_kernel_mixed_with_empty():
     check(b)
 
 
-def test_tiled_kernel_dense_one_image():
-    check(ot_batch(1, seed=1, dense=(1360, 1364), sigma=0.1))
+def test_dense_all_cells_one_image():
+    """Every cell of the darknet_tiny / darknet53 grids (BASELINE.json configs[2], variant 3b): streaming kernel."""
+    check(ot_batch(1, seed=1, dense=(1360, 1364), sigma=0.1), tol=parity.TOL_STREAM)
 
 
 @pytest.mark.parametrize("kind", ["small_zero_copy", "small_zero_copy_nowb", "small_memcpy", "tiled"])
@@ -139,9 +140,10 @@ def test_bad_arguments_fail_loudly():
 def test_large_path_kernels_match_oracle_d2(path, monkeypatch):
     """Both large-cloud kernels (streaming cooperative = default, tiled = KDOT_FORCE_PATH=tiled) on D = 2 problems."""
     monkeypatch.setenv("KDOT_FORCE_PATH", path)
-    check(ot_batch(3, seed=7, n_range=(40, 90), m_range=(50, 120), p_empty_teacher=0.0))
-    check(ot_batch(6, seed=9, n_range=(1, 70), m_range=(1, 70), p_empty_teacher=0.3))
-    check(ot_batch(4, seed=31, n_range=(33, 40), m_range=(33, 40)), reach=None, scaling=0.7)
+    tol = parity.TOL_STREAM if path == "stream" else parity.TOL
+    check(ot_batch(3, seed=7, n_range=(40, 90), m_range=(50, 120), p_empty_teacher=0.0), tol=tol)
+    check(ot_batch(6, seed=9, n_range=(1, 70), m_range=(1, 70), p_empty_teacher=0.3), tol=tol)
+    check(ot_batch(4, seed=31, n_range=(33, 40), m_range=(33, 40)), tol=tol, reach=None, scaling=0.7)
 
 
 @pytest.mark.parametrize("n_range,m_range", [((16, 16), (16, 16)), ((16, 17), (16, 17)), ((3, 40), (2, 24)),
@@ -150,7 +152,8 @@ def test_default_dispatch_around_the_kernel_boundaries(n_range, m_range, monkeyp
     """No path forced: 32 | 33 points (register kernel -> CTA-resident tiled kernel) and 256 | 257 points
     (tiled -> streaming) give oracle-matching results on either side; the batch maximum decides for every image."""
     monkeypatch.delenv("KDOT_FORCE_PATH", raising=False)
-    check(ot_batch(5, seed=sum(n_range) + 3 * sum(m_range), n_range=n_range, m_range=m_range, p_empty_teacher=0.2))
+    tol = parity.TOL_STREAM if n_range[1] + m_range[1] > 256 else parity.TOL
+    check(ot_batch(5, seed=sum(n_range) + 3 * sum(m_range), n_range=n_range, m_range=m_range, p_empty_teacher=0.2), tol=tol)
 
 
 @pytest.mark.parametrize("dense,sigma,B", [((600, 640), 0.005, 2), ((900, 300), 0.3, 1), ((4200, 150), 0.1, 1)])
@@ -170,9 +173,11 @@ def test_stream_kernel_sorted_staging_and_exact_tile_skipping(dense, sigma, B):
     o = sinkhorn_analytic.kdot_fwd_bwd_f64(b["xs"], b["ws"], b["xt"], b["wt"], cu_seqlens(b["pos_per_img"]),
                                            cu_seqlens(b["pos_per_img_t"]), B, 2)
     assert np.array_equal(out["nits"].cpu().numpy(), o["nits"])
-    assert parity.rel(out["loss_per_img"].cpu().numpy(), o["loss_per_img"]) < 2e-6
-    assert parity.rel(out["grad_ws"].cpu().numpy(), o["grad_ws"]) < 5e-5
-    assert parity.rel(out["grad_xs"].cpu().numpy(), o["grad_xs"]) < 5e-3
+    e_l, e_w = parity.rel(out["loss_per_img"].cpu().numpy(), o["loss_per_img"]), parity.rel(out["grad_ws"].cpu().numpy(), o["grad_ws"])
+    e_x, q_x = parity.rel(out["grad_xs"].cpu().numpy(), o["grad_xs"]), parity.rel_quantile(out["grad_xs"].cpu().numpy(), o["grad_xs"])
+    print(f"\nstream {dense} sigma {sigma}: loss {e_l:.2e} d/dalpha {e_w:.2e} d/dx {e_x:.2e} (99.9 % quantile {q_x:.2e})")
+    assert e_l < 2e-6 and e_w < 5e-5
+    assert e_x <= parity.TOL_STREAM and q_x <= parity.TOL / 2
     # run-to-run reproducibility of the sorted path (deterministic ranks, fixed-order reductions)
     t2 = {k: torch.from_numpy(b[k]).to(dev) for k in ("xs", "ws", "xt", "wt")}
     out2 = ot_loss_batched(t2["xs"], t2["ws"], t2["xt"], t2["wt"], b["pos_per_img"], b["pos_per_img_t"], OTConfig())
@@ -193,9 +198,11 @@ def test_stream_kernel_clouds_beyond_shared_memory():
     o = sinkhorn_analytic.kdot_fwd_bwd_f64(b["xs"], b["ws"], b["xt"], b["wt"], cu_seqlens(b["pos_per_img"]),
                                            cu_seqlens(b["pos_per_img_t"]), 1, 2)
     assert np.array_equal(out["nits"].cpu().numpy(), o["nits"])
+    e_x, q_x = parity.rel(out["grad_xs"].cpu().numpy(), o["grad_xs"]), parity.rel_quantile(out["grad_xs"].cpu().numpy(), o["grad_xs"])
+    print(f"\nstream 3500x3400: d/dx {e_x:.2e} (99.9 % quantile {q_x:.2e})")
     assert parity.rel(out["loss_per_img"].cpu().numpy(), o["loss_per_img"]) < 2e-6
     assert parity.rel(out["grad_ws"].cpu().numpy(), o["grad_ws"]) < 5e-5
-    assert parity.rel(out["grad_xs"].cpu().numpy(), o["grad_xs"]) < 5e-3
+    assert e_x <= parity.TOL_STREAM and q_x <= parity.TOL / 2
 
 
 @pytest.mark.parametrize("D,blur", [(16, 0.05), (16, 0.01), (3, 0.01), (8, 0.001)])

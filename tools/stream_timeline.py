@@ -33,6 +33,7 @@ def main():
     t = buf.cpu().numpy()
     t0 = t[0]
     hdr = (t[:5] - t0) / 1e3
+    print("float64 sub-tiles: gradient-round screened %d -> evaluated %d; potential rounds evaluated %d" % (t[5], t[7], t[6]))
     print(f"N=M={n} images={nimg}: phase0a end {hdr[1]:.1f} us, phase0b end {hdr[2]:.1f}, rounds end {hdr[3]:.1f}, after grid.sync {hdr[4]:.1f}")
     rounds = int(db.nits.cpu().numpy().max()) + 2
     R = 2
