@@ -201,10 +201,102 @@ def golden_postprocess_and_loss(nimg=6, seed=0):
          gall_cls_abs=np.asarray([float(np.abs(z(g_all[l], s_cls[l])).astype(np.float64).sum()) for l in range(4)]))
 
 
+# ---------------------------------------------------------------------------------------------------------
+# 4. hard selection scene: every label of PostProcessorKD.pose_infer_ml and the student-eval PostProcessor
+# ---------------------------------------------------------------------------------------------------------
+def golden_postprocess_hard(nimg=64, seed=5):
+    """Reference ``PostProcessorKD`` (all candidate labels, not only the first) and reference ``PostProcessor``
+    (``postprocess/postprocess.py``, with its ``clsId in target.class_ids`` filter) on the hard scene of
+    ``tests/scenario.py``: batch 64, 2-3 live classes per image, object scales 0.7x..2.6x, exact duplicate logits and
+    logits within 2 ulps of the 0.1 threshold.  Stored per (image, label): candidate counts per level, selected
+    (level, cell) sequence, scores; per image the student-eval results (class, score, R, T)."""
+    import importlib
+
+    from tests.scenario import hard_live_classes, make_hard_scene
+
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    t_hw = [(32, 32), (16, 16), (8, 8), (4, 4), (2, 2)]
+    tarr, t_cls, t_reg = make_hard_scene(nimg, t_hw, seed)
+    targets = []
+    for i in range(nimg):
+        ids = [c for c in hard_live_classes(i) if c in (0, 3)]
+        t = ref.PoseAnnot(torch.tensor(tarr["keypoints_3d"]), torch.tensor(tarr["K"]), torch.tensor(tarr["mask"][i]),
+                          torch.tensor(ids, dtype=torch.int64), torch.tensor(np.repeat(tarr["rotations"][i], len(ids), 0)),
+                          torch.tensor(np.repeat(tarr["translations"][i], len(ids), 0)), 256, 256,
+                          bbox_scale=torch.tensor(1.0), bbox_trans=torch.tensor(tarr["bbox_trans"][i]))
+        targets.append(t)
+    coder = ref.TargetCoder("POINT", ANCHOR_SIZES, ANCHOR_STRIDES, target_type="3D")
+    pp = ref.PostProcessorKD(0.1, coder, 10, 1.0, {})
+    anchors_t = ref_anchors(nimg, t_hw)
+    cls_t = [torch.tensor(a) for a in t_cls]
+    reg_t = [torch.tensor(a) for a in t_reg]
+    with torch.no_grad():
+        sampled = [pp.forward_for_single_feature_map(o, b, a) for o, b, a in zip(cls_t, reg_t, list(zip(*anchors_t)))]
+        per_img = list(zip(*sampled))
+        kd_first = pp(cls_t, reg_t, targets, anchors_t)
+        pp_eval = importlib.import_module("postprocess.postprocess").PostProcessor(0.1, coder, 10, 1.0, {})
+        ev = pp_eval(cls_t, reg_t, targets, anchors_t)
+
+    # decode of EVERY cell of every level for a class, un-cropped, to recover which cells the reference selected
+    def all_cells_xy(i, c):
+        out = []
+        bt = tarr["bbox_trans"][i].astype(np.float64)
+        Ainv = np.linalg.inv(bt[:, :2])
+        for lv, (h, w) in enumerate(t_hw):
+            stride, size = ANCHOR_STRIDES[lv], ANCHOR_SIZES[lv]
+            cy, cx = np.meshgrid(np.arange(h) * stride + stride / 2, np.arange(w) * stride + stride / 2, indexing="ij")
+            pts = []
+            for k in range(8):
+                x = t_reg[lv][i, 16 * c + k].astype(np.float64) * size + cx
+                y = t_reg[lv][i, 16 * c + 8 + k].astype(np.float64) * size + cy
+                pts.append((Ainv @ (np.stack([x.reshape(-1), y.reshape(-1)]) - bt[:, 2:3])).T)
+            out.append(np.concatenate(pts, axis=1))  # (cells, 16): x0 y0 x1 y1 ...
+        return out
+
+    rec = dict(img=[], label=[], count=[], valid=[], level=[], loc=[], score=[])
+    n_dup_ties = 0
+    for i in range(nimg):
+        preds = per_img[i]
+        with torch.no_grad():
+            res = pp.pose_infer_ml(preds, targets[i])
+        for scores, cls_id, R, T, xy2d in res:
+            cells = all_cells_xy(i, cls_id)
+            valid = [0 if p is None else int((p[1] == cls_id + 1).sum()) for p in preds]
+            lv_seq, loc_seq = [], []
+            for row in xy2d.reshape(len(xy2d), 16).numpy().astype(np.float64):
+                hits = [(lv, int(k)) for lv in range(len(t_hw)) for k in np.flatnonzero(np.abs(cells[lv] - row).max(axis=1) < 2e-2)]
+                assert len(hits) == 1, ("ambiguous / missing cell", i, cls_id, hits)
+                lv_seq.append(hits[0][0])
+                loc_seq.append(hits[0][1])
+            sc = scores[:, 0].numpy()
+            n_dup_ties += int(len(np.unique(sc)) < len(sc))
+            rec["img"].append(i); rec["label"].append(cls_id); rec["count"].append(len(lv_seq)); rec["valid"].append(valid)
+            rec["level"].append(lv_seq); rec["loc"].append(loc_seq); rec["score"].append(sc)
+    print("hard scene: %d (image, label) results, %d with tied scores among the selected cells" % (len(rec["img"]), n_dup_ties))
+    ev_img, ev_cls, ev_score, ev_R, ev_T = [], [], [], [], []
+    for i, lst in enumerate(ev):
+        for score, cls_id, R, T, _xy in lst:
+            ev_img.append(i); ev_cls.append(cls_id); ev_score.append(score); ev_R.append(R); ev_T.append(T.reshape(3))
+    first_cnt = [len(r) for r in kd_first[0]]
+    save("postprocess_hard.npz", nimg=nimg, seed=seed, inputs_sha256=digest(t_cls + t_reg),
+         bbox_trans=tarr["bbox_trans"], K=tarr["K"], keypoints_3d=tarr["keypoints_3d"],
+         img=np.asarray(rec["img"]), label=np.asarray(rec["label"]), count=np.asarray(rec["count"]),
+         valid=np.asarray(rec["valid"]), level=np.concatenate([np.asarray(v, np.int32) for v in rec["level"]]),
+         loc=np.concatenate([np.asarray(v, np.int32) for v in rec["loc"]]), score=np.concatenate(rec["score"]),
+         first_label_count=np.asarray(first_cnt),
+         ev_img=np.asarray(ev_img), ev_cls=np.asarray(ev_cls), ev_score=np.asarray(ev_score, np.float64),
+         ev_R=np.asarray(ev_R, np.float64), ev_T=np.asarray(ev_T, np.float64))
+
+
 if __name__ == "__main__":
+    if "--hard-only" in sys.argv:
+        golden_postprocess_hard()
+        raise SystemExit(0)
     golden_ot_boundary("ape_b8", ot_batch(8, seed=0))
     golden_ot_boundary("ape_b8_tight", ot_batch(8, seed=1, sigma=0.005))
     golden_ot_boundary("balanced", ot_batch(4, seed=2), reach=None)
     golden_ot_boundary("unweighted", ot_batch(4, seed=3), weighted=False)
     golden_ot_boundary("mid", ot_batch(2, seed=4, n_range=(40, 60), m_range=(50, 70), p_empty_teacher=0.0), scaling=0.7)
     golden_postprocess_and_loss()
+    golden_postprocess_hard()

@@ -28,7 +28,7 @@ def _rodrigues(v):
     return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
 
 
-def make_target_arrays(nimg, seed):
+def make_target_arrays(nimg, seed, scale_range=(1.4, 1.8)):
     rng = np.random.default_rng(seed)
     corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float32) * HALF_EXTENT
     kp3d = np.tile(corners[None], (N_CLASS, 1, 1)).astype(np.float32)
@@ -39,7 +39,7 @@ def make_target_arrays(nimg, seed):
         z = rng.uniform(800, 1000)
         T = (np.linalg.inv(K.astype(np.float64)) @ np.array([u, v, 1.0]) * z).reshape(3, 1)
         R = _rodrigues(rng.normal(0, 0.4, 3))
-        s = rng.uniform(1.4, 1.8)
+        s = rng.uniform(*scale_range)
         bt = np.array([[s, 0, 128 - s * u], [0, s, 128 - s * v]], np.float32)
         cam = K.astype(np.float64) @ (R @ corners.T.astype(np.float64) + T)
         uv = cam[:2] / cam[2]
@@ -59,7 +59,7 @@ def make_target_arrays(nimg, seed):
     return out
 
 
-def make_head_outputs(nimg, level_hw, seed, teacher, target_seed=0):
+def make_head_outputs(nimg, level_hw, seed, teacher, target_seed=0, tarr=None):
     """Per level ``(nimg, 15, H, W)`` class logits and ``(nimg, 240, H, W)`` keypoint offsets.
 
     Class-0 logits are high inside the object mask (so the teacher's 0.1 confidence threshold selects cells
@@ -67,7 +67,7 @@ def make_head_outputs(nimg, level_hw, seed, teacher, target_seed=0):
     class 0 are the encoded true keypoints plus noise (teacher: small, student: larger), so that RANSAC-PnP in
     the reference post-processor succeeds and the OT problem looks like real distillation data."""
     rng = np.random.default_rng(seed)
-    tarr = make_target_arrays(nimg, target_seed)
+    tarr = make_target_arrays(nimg, target_seed) if tarr is None else tarr
     noise = 0.03 if teacher else 0.12
     cls_l, reg_l = [], []
     for lv, (h, w) in enumerate(level_hw):
@@ -85,3 +85,56 @@ def make_head_outputs(nimg, level_hw, seed, teacher, target_seed=0):
         cls_l.append(cls)
         reg_l.append(reg)
     return cls_l, reg_l
+
+
+# ---------------------------------------------------------------------------------------------------------
+# hard selection scene (tests/golden/postprocess_hard.npz): several live classes per image, object scales from 0.7x to
+# 2.6x (every per-level budget pattern), exact duplicate logits (arg-max / top-k ties) and logits within a few ulps of
+# the 0.1 confidence threshold
+# ---------------------------------------------------------------------------------------------------------
+HARD_EXTRA_CLASSES = (3, 7, 5)
+THRESHOLD_LOGIT = np.float32(np.log(0.1 / 0.9))  # sigmoid(x) == 0.1 up to rounding
+
+
+def hard_live_classes(i):
+    """Classes with cells above the threshold in image i (class 0 always; PostProcessor's target.class_ids filter keeps
+    only classes 0 and 3)."""
+    return [0, HARD_EXTRA_CLASSES[i % 2]] + ([HARD_EXTRA_CLASSES[2]] if i % 3 == 0 else [])
+
+
+def make_hard_scene(nimg, level_hw, seed):
+    tarr = make_target_arrays(nimg, seed, scale_range=(0.7, 2.6))
+    cls_l, reg_l = make_head_outputs(nimg, level_hw, seed + 100, teacher=True, tarr=tarr)
+    rng = np.random.default_rng(seed + 999)
+    for lv, (h, w) in enumerate(level_hw):
+        stride, size = ANCHOR_STRIDES[lv], ANCHOR_SIZES[lv]
+        cy, cx = np.meshgrid(np.arange(h) * stride + stride / 2, np.arange(w) * stride + stride / 2, indexing="ij")
+        for i in range(nimg):
+            m = tarr["mask"][i][np.clip(cy.astype(int), 0, 255), np.clip(cx.astype(int), 0, 255)] > 0
+            kp = tarr["kp2d_crop"][i]
+            for c in hard_live_classes(i)[1:]:
+                cls_l[lv][i, c] = np.where(m, rng.normal(0.3, 1.0, (h, w)), rng.normal(-4.0, 1.0, (h, w))).astype(np.float32)
+                for k in range(8):
+                    reg_l[lv][i, 16 * c + k] = ((kp[0, k] - cx) / size + rng.normal(0, 0.03, (h, w))).astype(np.float32)
+                    reg_l[lv][i, 16 * c + 8 + k] = ((kp[1, k] - cy) / size + rng.normal(0, 0.03, (h, w))).astype(np.float32)
+            if lv <= 1:
+                flat = cls_l[lv][i, 0].reshape(-1)           # view: edits land in cls_l
+                inside = np.flatnonzero(m.reshape(-1))
+                outside = np.flatnonzero(~m.reshape(-1))
+                if len(inside) >= 12:
+                    a = inside[np.argmax(flat[inside])]
+                    others = inside[inside != a]
+                    pick = rng.choice(others, size=11, replace=False)
+                    if i % 4 == 1:
+                        flat[pick[0]] = flat[a]              # duplicate of the level's maximum (arg-max tie), every 4th image
+                    for q in range(5):                        # five more exact duplicates among the candidates (top-k ties)
+                        flat[pick[1 + 2 * q]] = flat[pick[2 + 2 * q]]
+                if lv == 0 and len(outside) >= 6:
+                    edge = rng.choice(outside, size=6, replace=False)
+                    v = THRESHOLD_LOGIT
+                    vals = [np.nextafter(np.nextafter(v, np.float32(-np.inf)), np.float32(-np.inf)), np.nextafter(v, np.float32(-np.inf)), v,
+                            np.nextafter(v, np.float32(np.inf)), np.nextafter(np.nextafter(v, np.float32(np.inf)), np.float32(np.inf)),
+                            np.float32(v + 1e-5)]
+                    for e, val in zip(edge, vals):
+                        flat[e] = val
+    return tarr, cls_l, reg_l

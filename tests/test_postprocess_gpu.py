@@ -114,3 +114,103 @@ def test_student_eval_postprocessor_same_selection():
     targets[0].class_ids = torch.tensor([3])
     out = pp([torch.from_numpy(a).to(dev) for a in t_cls], [torch.from_numpy(a).to(dev) for a in t_reg], targets, None)
     assert out[0] == [] and len(out[1]) == 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# hard scene (tests/golden/postprocess_hard.npz): produced by the reference's PostProcessorKD.pose_infer_ml for EVERY
+# candidate label and by the reference's student-eval PostProcessor (tests/golden/make_golden.py --hard-only)
+# ---------------------------------------------------------------------------------------------------------
+HARD = os.path.join(os.path.dirname(__file__), "golden", "postprocess_hard.npz")
+
+
+def _hard_inputs():
+    z = np.load(HARD)
+    nimg, seed = int(z["nimg"]), int(z["seed"])
+    tarr, t_cls, t_reg = scenario.make_hard_scene(nimg, T_HW, seed)
+    assert doubles.digest(t_cls + t_reg) == str(z["inputs_sha256"]), "synthetic inputs differ from the fixture's"
+    dev = torch.device("cuda:0")
+    return z, nimg, [torch.from_numpy(a).to(dev) for a in t_cls], [torch.from_numpy(a).to(dev) for a in t_reg]
+
+
+def test_hard_scene_every_label_bit_exact():
+    """Batch 64, 2-3 live classes per image, object scales 0.7x..2.6x (all budget patterns), exact duplicate logits
+    (arg-max and top-k ties) and logits within 2 ulps of the 0.1 threshold: candidate counts per level, the number of
+    selected cells and the (level, cell) sequence of every (image, label) the reference produced a pose for."""
+    from kd_6d_pose_adlp_b200.postprocess.postprocess_kd import select_cells
+
+    z, nimg, cls, reg = _hard_inputs()
+    sel = select_cells(cls, reg, scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES, 0.1, 10, 1.0)
+    torch.cuda.synchronize()
+    cap, ncls = sel["cap"], sel["ncls"]
+    count = sel["sel_count"].cpu().numpy().reshape(nimg, ncls)
+    valid = sel["valid_cnt"].cpu().numpy().reshape(nimg, ncls, -1)
+    level = sel["sel_level"].cpu().numpy().reshape(nimg, ncls, cap)
+    loc = sel["sel_loc"].cpu().numpy().reshape(nimg, ncls, cap)
+    score = sel["sel_score"].cpu().numpy().reshape(nimg, ncls, cap)
+    o = 0
+    labels_seen = set()
+    planes = [t.cpu().numpy().reshape(nimg, ncls, -1) for t in cls]
+    n_unique = n_tied = n_best_tie = 0
+    for i, c, n, v in zip(z["img"], z["label"], z["count"], z["valid"]):
+        labels_seen.add(int(c))
+        assert valid[i, c].tolist() == v.tolist(), ("candidates per level", i, c)          # threshold edge cells included
+        if i % 4 == 1 and c == 0 and count[i, c] != n:
+            # every 4th image carries an exact duplicate of its best class-0 logit: WHICH of the two tied cells the
+            # reference's argmax-after-unsorted-topk (postprocess_kd.py:42,135) returns is implementation-defined, and
+            # the box size -- hence the per-level budget -- is taken from that cell.  The kernel takes the lower index
+            # (torch.argmax's documented first-occurrence rule on the natural order); test_budget_and_argmax_against_
+            # numpy_restatement pins that rule.
+            n_best_tie += 1
+            o += n
+            continue
+        assert count[i, c] == n, ("selected cells", i, c, count[i, c], n)
+        assert np.array_equal(level[i, c, :n], z["level"][o:o + n]), ("levels", i, c)
+        assert np.abs(score[i, c, :n] - z["score"][o:o + n]).max() < 2e-6
+        # Cells: identical wherever the logit is unique in its level plane.  Among EXACTLY tied logits the reference's
+        # order is whatever its two-stage top-k yields (topk(sorted=False) over the candidates, then topk again,
+        # postprocess_kd.py:42,154 -- implementation-defined, and different between torch's CPU and CUDA top-k); the
+        # kernel's rule is "lower cell index first".  There the selected LOGIT VALUES must still be the same sequence.
+        for k in range(n):
+            lv, mine, theirs = int(level[i, c, k]), int(loc[i, c, k]), int(z["loc"][o + k])
+            plane = planes[lv][i, c]
+            assert plane[mine] == plane[theirs], ("selected value", i, c, k)
+            if (plane == plane[theirs]).sum() == 1:
+                assert mine == theirs, ("cell", i, c, k, mine, theirs)
+                n_unique += 1
+            else:
+                n_tied += 1
+        o += n
+    assert o == len(z["loc"]) and labels_seen == {0, 3, 5, 7}
+    assert n_unique > 1000 and n_tied > 40 and n_best_tie <= 8, (n_unique, n_tied, n_best_tie)   # the fixture really contains ties
+
+
+def test_hard_scene_teacher_and_student_postprocessors():
+    """The drop-in post-processors on the hard scene: PostProcessorKD keeps the first label's cells (count per image as
+    in the reference run), PostProcessor applies the target.class_ids filter and returns the reference's poses."""
+    from kd_6d_pose_adlp_b200.postprocess.postprocess_kd import PostProcessor, PostProcessorKD
+    from kd_6d_pose_adlp_b200.target_coder import TargetCoder
+
+    z, nimg, cls, reg = _hard_inputs()
+    targets = []
+    for i in range(nimg):
+        t = doubles.Target(torch.tensor(z["K"]), torch.tensor(z["keypoints_3d"]), torch.tensor(z["bbox_trans"][i]))
+        t.class_ids = torch.tensor([c for c in scenario.hard_live_classes(i) if c in (0, 3)])
+        targets.append(t)
+    coder = TargetCoder("POINT", scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES)
+    res = PostProcessorKD(0.1, coder, 10, 1.0, {})(cls, reg, targets, None)
+    assert [len(r) for r in res[0]] == z["first_label_count"].tolist()
+    out = PostProcessor(0.1, coder, 10, 1.0, {})(cls, reg, targets, None)
+    got = [(i, int(r[1]), float(r[0]), np.asarray(r[2]), np.asarray(r[3]).reshape(3)) for i, lst in enumerate(out) for r in lst]
+    assert [(g[0], g[1]) for g in got] == list(zip(z["ev_img"].tolist(), z["ev_cls"].tolist()))   # same (image, class) list
+    assert set(z["ev_cls"].tolist()) == {0, 3}                                                       # 5 and 7 were filtered
+    dR, dT = [], []
+    for g, s, R, T in zip(got, z["ev_score"], z["ev_R"], z["ev_T"]):
+        assert abs(g[2] - s) < 2e-6
+        dR.append(np.abs(g[3] - R).max())
+        dT.append(np.abs(g[4] - T).max() / np.abs(T).max())
+    # RANSAC-EPnP (cv2, host, as in the reference): identical cell sequences give the same minimal sets and the same pose
+    # to solver precision; where exactly tied logits are ordered differently (see the test above) the 80 key-points
+    # arrive permuted, RANSAC samples other minimal sets and the pose moves within the ~1 px noise of the key-points
+    assert np.median(dR) < 1e-4 and np.median(dT) < 1e-4, (np.median(dR), np.median(dT))
+    assert max(dR) < 0.1 and max(dT) < 0.1, (max(dR), max(dT))
+    assert sum(d > 1e-3 for d in dR) <= len(dR) // 4, "only the entries with re-ordered ties may move"
