@@ -29,12 +29,8 @@ class KdotError(RuntimeError):
     pass
 
 
-def lib():
-    """The loaded shared library (loads on first use; raises if it was not built)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    path = os.environ.get("KDOT_LIB", LIB_PATH)  # tuning aid: alternative builds of the same ABI
+def load(path: str):
+    """dlopen a build of the C ABI and declare the prototypes of include/kdot.h on it."""
     if not os.path.exists(path):
         raise KdotError(
             f"{path} not found: the CUDA extension is not built and there is no CPU fallback. "
@@ -73,8 +69,15 @@ def lib():
     L.kdot_debug_set_clock_buffer.argtypes = [vp]
     L.kdot_measure_fp32_peak_tflops.restype = C.c_double
     L.kdot_measure_fp32_peak_tflops.argtypes = [i32, i32]
-    _lib = L
     return L
+
+
+def lib():
+    """The loaded shared library (loads on first use; raises if it was not built)."""
+    global _lib
+    if _lib is None:
+        _lib = load(os.environ.get("KDOT_LIB", LIB_PATH))  # KDOT_LIB: tuning aid, alternative builds of the same ABI
+    return _lib
 
 
 def check(rc: int, what: str):

@@ -232,6 +232,16 @@ __device__ __forceinline__ ImgSched image_schedule(float diam_f, const SchedPara
   ImgSched is;
   int len = 0;
   while (len < KDOT_SCHED_TABLE && eps0 * sp.pow_table[len] > sp.eps_final) ++len;
+  // Exact ties -- diam^p * scaling^(p k) == blur^p, e.g. scaling = 0.5 with diam / blur a power of two -- are decided
+  // by rounding: numpy's arange length is ceil((p ln blur - p ln diam) / (p ln scaling)), the loop above compares
+  // products of exponentials.  Within 1e-9 of a tie the length is taken from numpy's own formula (log route); nits is an
+  // integer output and has to be bit-exact.
+  {
+    const double last_in = len > 0 ? eps0 * sp.pow_table[len - 1] / sp.eps_final : 2.0;
+    const double first_out = len < KDOT_SCHED_TABLE ? eps0 * sp.pow_table[len] / sp.eps_final : 0.0;
+    if (last_in - 1.0 < 1e-9 || 1.0 - first_out < 1e-9)
+      return image_schedule_slow(diam, sp.p, sp.log_blur_p, sp.log_scaling_p, eps0);
+  }
   is.nits = len + 2;
   is.slow = 0;
   is.start = 0.0;

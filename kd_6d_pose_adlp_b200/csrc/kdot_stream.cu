@@ -227,12 +227,13 @@ __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_g
 // pts[d][strideP], ch[]).  The h arrays are rewritten every round by other SMs: cp.async.cg reads them from L2.
 // Tile-level skip data of one column set: bounding boxes and h maxima of its 32-column tiles.  For row i and a tile,
 //   hmax_tile + coef * dist^2(p_i, tile box)       (coef < 0)
-// bounds every soft-min argument of the row against the tile's columns from above; when it lies more than 140 below the
-// row's reference exponent for EVERY row of the warp, each ex2 of the tile would flush to exactly +0 in every lane
-// (128 = ex2.approx.ftz flush point, 12 more for the fp32 rounding of the bound), so the tile is skipped without
-// evaluating a single pair.  Intended to be bit-identical to evaluating it (only exact zeros are dropped); checked by an
-// A/B against a -DKDOT_NO_TILE_SKIP build (tools/ab_tile_skip.py: identical bits on three synthetic workloads), not by
-// the parity tests.
+// bounds every soft-min argument of the row against the tile's columns from above; when it lies more than 140 (plus a
+// magnitude-proportional rounding allowance, derived at the test itself) below the row's reference exponent for EVERY
+// row of the warp, each ex2 of the tile flushes to exactly +0 in every lane (-126 = ex2.approx.ftz flush point), so the
+// tile is skipped without evaluating a single pair: only exact zeros are dropped, the result is bit-identical to
+// evaluating everything.  tests/test_sinkhorn_gpu.py::test_tile_skipping_is_bit_exact checks that against the
+// -DKDOT_NO_TILE_SKIP build (libkdot_noskip.so: same order, seeds and arithmetic, every tile evaluated) on adversarial
+// clouds (clusters + far outliers, masses 1e-3 / 0.999, blur 1e-3..5e-2, N >> M).
 struct TileSkip {
   const float4* tbox;  // first tile of the column set: (min x, min y, max x, max y)
   const float* hmax;   // same tiles, current h buffer
@@ -474,7 +475,13 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
           const float px = -st[k].nx[0], py = -st[k].nx[D - 1];
           const float dx = fmaxf(fmaxf(bx.x - px, px - bx.z), 0.f);
           const float dy = fmaxf(fmaxf(bx.y - py, py - bx.w), 0.f);
-          far = far && (fmaf(coef, fmaf(dx, dx, dy * dy), hm) - st[k].mref < -140.f);
+          // b = fl(coef * fl(dist^2) + hmax) bounds every true argument h_j + coef |p_i - p_j|^2 of the sub-tile from above
+          // (coef < 0, |p_i - p_j| >= dist(p_i, box), h_j <= hmax) up to its own rounding, <= 2^-22 (|hmax| + |coef dist^2|);
+          // an evaluated argument fl(coef * fl(d^2) + h_j) exceeds its true value by at most the same expression with
+          // d in place of dist.  ex2.approx.ftz returns exactly +0 below -126, so "b - mref < -140 - 2^-20 (|hmax| +
+          // |coef dist^2|)" leaves 14 units plus twice the worst-case rounding: nothing but exact zeros is dropped.
+          const float cd = coef * fmaf(dx, dx, dy * dy);
+          far = far && ((cd + hm) - st[k].mref < -140.f - 9.5367e-7f * (fabsf(hm) + fabsf(cd)));
         }
         if (__all_sync(0xffffffffu, far)) dead |= 1u << sb;
       }

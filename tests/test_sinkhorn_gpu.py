@@ -267,3 +267,102 @@ def test_p1_distance_cost(blur, reach):
                 parity.report("grad_a", ad.grad.cpu().numpy(), refs["ref32"][2], refs["ref64"][2])]
         print("\n" + parity.fmt(rows))
         assert all(r["ok"] for r in rows), parity.fmt(rows)
+
+
+@pytest.mark.parametrize("kernel_points", [6, 60, 300])   # register / CTA-resident / streaming kernel
+def test_schedule_length_at_exact_ties(kernel_points):
+    """scaling = 0.5, blur = 2^-10 and a bounding-box diagonal of exactly 1, 1/2, 1/4: diam^2 * 0.25^k hits blur^2
+    EXACTLY, so the length of geomloss' epsilon schedule -- numpy's len(arange(2 ln diam, 2 ln blur, 2 ln 0.5)) + 2 -- is
+    decided by rounding.  nits is an integer output: it has to equal the oracle's np.arange-based value bit for bit."""
+    from kd_6d_pose_adlp_b200.ops import OTConfig, ot_loss_batched
+    from kd_6d_pose_adlp_b200.synthetic import cu_seqlens
+    from oracle import sinkhorn_analytic
+
+    rng = np.random.default_rng(kernel_points)
+    n = m = kernel_points
+    extents = [(0.25, 1.25), (0.25, 0.75), (0.5, 0.75), (0.125, 0.1875)]   # diagonals 1, 1/2, 1/4, 1/16 (y is constant)
+    xs = np.empty((len(extents) * n, 8, 2), np.float32)
+    xt = np.empty((len(extents) * m, 8, 2), np.float32)
+    for i, (lo, hi) in enumerate(extents):
+        for arr, cnt in ((xs, n), (xt, m)):
+            blk = arr[i * cnt:(i + 1) * cnt]
+            blk[..., 0] = rng.uniform(lo, hi, (cnt, 8)).astype(np.float32)
+            blk[..., 1] = 0.5
+        xs[i * n, :, 0] = lo          # the box is spanned exactly
+        xt[i * m, :, 0] = hi
+    ws = rng.uniform(0.1, 0.9, (len(extents) * n, 8)).astype(np.float32)
+    wt = rng.uniform(0.1, 0.9, (len(extents) * m, 8)).astype(np.float32)
+    pos_n, pos_m = [n] * len(extents), [m] * len(extents)
+    blur = 2.0 ** -10
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(a.copy()).to(dev)
+    out = ot_loss_batched(t(xs), t(ws), t(xt), t(wt), pos_n, pos_m, OTConfig(blur=blur, scaling=0.5), normalize=False)
+    torch.cuda.synchronize()
+    o = sinkhorn_analytic.kdot_fwd_bwd_f64(xs, ws, xt, wt, cu_seqlens(pos_n), cu_seqlens(pos_m), 8, 2, blur=blur, scaling=0.5,
+                                           normalize=False)
+    # the oracle's lengths come from np.arange itself; the expected values spell out what "tie" means here
+    for (lo, hi), nits in zip(extents, o["nits"]):
+        diam = np.float32(hi) - np.float32(lo)
+        want = len(np.arange(2 * np.log(float(diam)), 2 * np.log(blur), 2 * np.log(0.5))) + 2
+        assert nits == want
+    assert np.array_equal(out["nits"].cpu().numpy(), o["nits"]), (out["nits"].cpu().numpy(), o["nits"])
+    assert parity.rel(out["loss_per_img"].cpu().numpy(), o["loss_per_img"]) < 1e-5
+
+
+def _adversarial_clouds():
+    """Clouds built to break an over-eager skip rule: tight clusters with far outliers (a tile's box is huge while its
+    points are clumped), masses of 1e-3 next to 0.999 (log-weights 10 units apart inside a tile), N >> M and M >> N."""
+    rng = np.random.default_rng(123)
+    cases = []
+    for name, (n, m), blur in (("clusters+outliers", (700, 650), 1e-3), ("clusters+outliers", (700, 650), 1e-2),
+                               ("n>>m", (3000, 40), 1e-3), ("m>>n", (40, 2500), 5e-2), ("masses", (900, 900), 1e-3)):
+        B = 2
+        def cloud(k):
+            centres = rng.uniform(0.2, 0.8, (6, 1, 2))
+            pts = (centres[rng.integers(0, 6, k)] + 0.004 * rng.standard_normal((k, B, 2)))
+            far = rng.random(k) < 0.03                      # 3 % outliers anywhere in the frame
+            pts[far] = rng.uniform(0.0, 1.0, (int(far.sum()), B, 2))
+            return (pts * np.array([640.0, 480.0])).astype(np.float32)
+        xs, xt = cloud(n), cloud(m)
+        if name == "masses":
+            ws = np.where(rng.random((n, 1)) < 0.5, 1e-3, 0.999).astype(np.float32).repeat(B, 1)
+            wt = np.where(rng.random((m, 1)) < 0.5, 1e-3, 0.999).astype(np.float32).repeat(B, 1)
+        else:
+            ws = rng.uniform(0.05, 0.95, (n, 1)).astype(np.float32).repeat(B, 1)
+            wt = rng.uniform(0.05, 0.95, (m, 1)).astype(np.float32).repeat(B, 1)
+        cases.append((f"{name} {n}x{m} blur {blur}", xs, ws, xt, wt, blur))
+    return cases
+
+
+def test_tile_skipping_is_bit_exact():
+    """The streaming kernel's tile skipping drops only terms whose exponential is exactly +0: the shipped library and
+    the -DKDOT_NO_TILE_SKIP build of the same sources (libkdot_noskip.so, built by __graft_entry__.build(): same Morton
+    order, seeds and arithmetic, every tile evaluated) must agree BIT FOR BIT on loss, d/dx and d/dalpha."""
+    from kd_6d_pose_adlp_b200 import _lib
+    from kd_6d_pose_adlp_b200.build import NOSKIP_LIB_PATH
+
+    dev = torch.device("cuda:0")
+    libs = {"skip": _lib.lib(), "noskip": _lib.load(NOSKIP_LIB_PATH)}
+    for name, xs, ws, xt, wt, blur in _adversarial_clouds():
+        n, m, B = xs.shape[0], xt.shape[0], xs.shape[1]
+        res = {}
+        for tag, L in libs.items():
+            t = lambda a: torch.from_numpy(a.copy()).to(dev)
+            dxs, dws, dxt, dwt = t(xs), t(ws), t(xt), t(wt)
+            cu = torch.tensor([0, n, 0, m], dtype=torch.int32, device=dev)
+            loss = torch.empty(1, device=dev); valid = torch.empty(1, dtype=torch.int32, device=dev)
+            nits = torch.empty(1, dtype=torch.int32, device=dev)
+            gx, gw = torch.empty_like(dxs), torch.empty_like(dws)
+            nb = int(L.kdot_workspace_bytes(1, n, m, B, 2))
+            wsp = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+            rc = L.kdot_sinkhorn_fwd_bwd(dxs.data_ptr(), dws.data_ptr(), dxt.data_ptr(), dwt.data_ptr(), cu[:2].data_ptr(),
+                                         cu[2:].data_ptr(), 1, B, 2, n, m, 0, 2.0, blur, 0.5, 0.5, 640.0, 480.0, 1,
+                                         loss.data_ptr(), None, valid.data_ptr(), gx.data_ptr(), gw.data_ptr(), nits.data_ptr(),
+                                         wsp.data_ptr(), nb, torch.cuda.current_stream(dev).cuda_stream)
+            assert rc == 0, L.kdot_last_error()
+            torch.cuda.synchronize()
+            res[tag] = (loss.cpu().numpy(), gx.cpu().numpy(), gw.cpu().numpy(), int(nits.cpu()[0]))
+        a, b = res["skip"], res["noskip"]
+        assert a[3] == b[3] and np.isfinite(a[0]).all() and np.isfinite(a[1]).all(), name
+        for k, what in enumerate(("loss", "d/dx", "d/dalpha")):
+            assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), f"{name}: {what} differs between the skipping and the non-skipping build"
