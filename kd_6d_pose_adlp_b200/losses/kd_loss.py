@@ -67,12 +67,18 @@ def _reference_visualizer(pred_xy, pred_t_xy, s_cls, t_cls, step, vis_dir, pos_s
         from tools.visualizer import vis_pxpy_post_train, vis_pxpy_post_train_weight
     except Exception:
         return False
-    if s_cls is not None:
-        vis_pxpy_post_train_weight(pred_xy, pred_t_xy, s_cls.reshape(-1, 1), t_cls.reshape(-1, 1), step, save_dir=vis_dir,
-                                   pos_per_img_1=pos_s, pos_per_img_2=pos_t, loss=losses)
-    else:
-        vis_pxpy_post_train(pred_xy, pred_t_xy, step, save_dir=vis_dir, pos_per_img_1=pos_s, pos_per_img_2=pos_t,
-                            loss=losses)
+    try:
+        if s_cls is not None:
+            vis_pxpy_post_train_weight(pred_xy, pred_t_xy, s_cls.reshape(-1, 1), t_cls.reshape(-1, 1), step, save_dir=vis_dir,
+                                       pos_per_img_1=pos_s, pos_per_img_2=pos_t, loss=losses)
+        else:
+            vis_pxpy_post_train(pred_xy, pred_t_xy, step, save_dir=vis_dir, pos_per_img_1=pos_s, pos_per_img_2=pos_t,
+                                loss=losses)
+    except Exception as exc:  # a broken plotting stack must not take the training step down with it
+        import warnings
+
+        warnings.warn(f"KDPoseLoss: the reference visualiser failed at step {step} ({exc!r}); plots skipped")
+        return False
     return True
 
 

@@ -66,9 +66,11 @@ def test_losses_and_gradients_match_reference():
         if np.abs(ref_c).max() > 0:
             assert np.abs(got_c - ref_c).max() <= 1e-4 * np.abs(ref_c).max()
         if np.abs(ref_r).max() > 0:
-            # d/d(offsets) inherits the fp32 noise of the REFERENCE's own d/dx (2e-4..6e-3 rel. at eps = 1e-6,
-            # SURVEY.md fact 3): the OT-boundary tests arbitrate that tensor against the fp64 oracle.
-            assert np.abs(got_r - ref_r).max() <= 1e-2 * np.abs(ref_r).max()
+            # The golden d/d(offsets) was produced by the reference's fp32 op sequence, whose own d/dx is 2e-4..6e-3
+            # (rel. max-norm) away from exact arithmetic at eps = 1e-6 (2.8e-3 on this batch,
+            # tests/golden/ot_boundary_ape_b8.npz: ref32 vs ref64) while the kernel is within 2e-5 of fp64
+            # (tests/test_golden_gpu.py asserts that).  5e-3 is therefore the reference's noise, not the kernel's.
+            assert np.abs(got_r - ref_r).max() <= 5e-3 * np.abs(ref_r).max()
     # the weighted total of the three losses, as train_kd.py combines them: focal-loss gradient on every class logit,
     # regression + distillation gradient on the positive cells' offsets (through the fused gather/decode epilogue)
     for l in range(4):
@@ -76,7 +78,7 @@ def test_losses_and_gradients_match_reference():
         got_r = np.zeros_like(ref_r) if g_all[4 + l] is None else g_all[4 + l].cpu().numpy()
         assert np.array_equal(np.flatnonzero(got_r), np.flatnonzero(ref_r))
         if np.abs(ref_r).max() > 0:
-            assert np.abs(got_r - ref_r).max() <= 1e-2 * np.abs(ref_r).max()
+            assert np.abs(got_r - ref_r).max() <= 5e-3 * np.abs(ref_r).max()   # see above: the reference's fp32 noise
         got_c = g_all[l].cpu().numpy().astype(np.float64)
         assert abs(got_c.sum() - z["gall_cls_sum"][l]) <= 1e-4 * z["gall_cls_abs"][l]
         assert abs(np.abs(got_c).sum() - z["gall_cls_abs"][l]) <= 1e-4 * z["gall_cls_abs"][l]
