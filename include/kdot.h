@@ -186,6 +186,29 @@ int kdot_gather_decode_bwd(const float* g_xy, const int32_t* hw_lvl, int nlvl, i
                            const int64_t* pos_inds, const int64_t* cls_label, const float* anchors,
                            const float* bbox_trans, int npos, float* const* g_reg_lvl, void* cuda_stream);
 
+/*
+ * The two dense losses beside the OT term in KDPoseLoss.__call__, forward + gradient fused.
+ *
+ * kdot_focal_loss_fwd_bwd: SigmoidFocalLoss.forward(pred_cls_flatten[valid], labels[valid]) of losses/loss.py:12-40
+ * (called at losses/kd_loss.py:134) without flattening anything: cls_lvl[l] -> (nimg, C, H_l, W_l) logits (host array
+ * of device pointers), labels[nimg * cells] int64 in the reference's label order (-1 ignored, 0 background, c + 1
+ * positive of class c; losses/loss.py:246-252).  Writes loss[0] = sum over all non-ignored (cell, class) pairs and,
+ * when g_cls_lvl != NULL, d loss / d logit into per-level gradients of the same shape (0 at ignored cells).
+ * workspace: kdot_focal_workspace_bytes() bytes whose first 16 are ZERO on entry (the kernel leaves them zero).
+ * The sum is reduced in a fixed order: bit-reproducible run to run.
+ *
+ * kdot_reg3d_loss_fwd_bwd: the 3-D object-space regression loss of losses/kd_loss.py:57-71 on the decoded key-points:
+ * xy[npos*8][2] (kd_loss.py:50), target3d[npos][8][3] (aux_3D_in_camera_frame of the positive cells), diam_cell[npos]
+ * (MESH_DIAMETERS[class]), kinv9_host = inverse(INTERNAL_K) row-major (HOST array).  Writes loss_cell[npos]
+ * (the per-cell `losses` of kd_loss.py:69-70; the reference returns their sum) and g_xy = d(sum)/d(xy).
+ */
+int kdot_focal_loss_fwd_bwd(const float* const* cls_lvl, const int32_t* hw_lvl, int nlvl, int nimg, int C,
+                            const int64_t* labels, float gamma, float alpha, float* loss, float* const* g_cls_lvl,
+                            void* workspace, size_t workspace_bytes, void* cuda_stream);
+size_t kdot_focal_workspace_bytes(void);
+int kdot_reg3d_loss_fwd_bwd(const float* xy, const float* target3d, const float* diam_cell, const float* kinv9_host,
+                            int npos, float* loss_cell, float* g_xy, void* cuda_stream);
+
 /* Diagnostics */
 const char* kdot_last_error(void);
 int kdot_version(void);

@@ -20,6 +20,7 @@ EXPORTS = (
     "kdot_sinkhorn_fwd_bwd", "kdot_kernel_mmd_fwd_bwd", "kdot_workspace_bytes", "kdot_workspace_bytes_ex", "kdot_host_ctx_create", "kdot_host_ctx_destroy",
     "kdot_sinkhorn_fwd_bwd_host", "kdot_host_ctx_last_traffic", "kdot_host_ctx_last_timing", "kdot_select_cells", "kdot_gather_decode_fwd", "kdot_gather_decode_bwd", "kdot_last_error",
     "kdot_version", "kdot_launch_count", "kdot_measure_fp32_peak_tflops", "kdot_debug_set_clock_buffer",
+    "kdot_focal_loss_fwd_bwd", "kdot_focal_workspace_bytes", "kdot_reg3d_loss_fwd_bwd",
 )
 
 _lib = None
@@ -67,6 +68,12 @@ def load(path: str):
     L.kdot_gather_decode_bwd.restype = i32
     L.kdot_gather_decode_bwd.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]
     L.kdot_debug_set_clock_buffer.argtypes = [vp]
+    L.kdot_focal_loss_fwd_bwd.restype = i32
+    L.kdot_focal_loss_fwd_bwd.argtypes = [vp, vp, i32, i32, i32, vp, f32, f32, vp, vp, vp, sz, vp]
+    L.kdot_focal_workspace_bytes.restype = sz
+    L.kdot_focal_workspace_bytes.argtypes = []
+    L.kdot_reg3d_loss_fwd_bwd.restype = i32
+    L.kdot_reg3d_loss_fwd_bwd.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
     L.kdot_measure_fp32_peak_tflops.restype = C.c_double
     L.kdot_measure_fp32_peak_tflops.argtypes = [i32, i32]
     return L

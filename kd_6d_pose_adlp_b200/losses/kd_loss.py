@@ -19,7 +19,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from ..ops import OTLossFunction, gather_decode
+from ..ops import FocalLossFunction, OTLossFunction, Reg3dLossFunction, gather_decode
 from ..samples_loss import SamplesLoss
 
 INF = 100000000
@@ -122,23 +122,16 @@ def make_kd_pose_loss(base):
             # in the step itself); KDOT_SYNC_STATUS=1 checks right after the launch instead
             self._pending_status = None
 
-        # -- the 3-D regression loss of kd_loss.py:52-71 (not the hot path; same math, stock torch ops) -----
+        # -- the 3-D regression loss of kd_loss.py:52-71: one fused forward + backward launch (kdot_reg3d_loss_fwd_bwd) --
         def _object_space_reg_loss(self, pred_xy, target_3d, cls_labels):
             if not isinstance(self.diameters, torch.Tensor):
                 self.diameters = torch.FloatTensor(self.diameters).to(device=pred_xy.device).view(-1)
             if not isinstance(self.internal_K, torch.Tensor):
                 self.internal_K = torch.FloatTensor(self.internal_K).to(device=pred_xy.device).view(3, 3)
-            n_cell = cls_labels.shape[0]
-            diam = self.diameters[cls_labels.view(-1, 1).repeat(1, 8 * 3).view(-1, 3, 1)]
-            homog = torch.cat((pred_xy.t(), torch.ones_like(pred_xy[:, 0]).view(1, -1)), dim=0)
-            ray = torch.inverse(self.internal_K).mm(homog).t()
-            proj = torch.bmm(ray.view(-1, 3, 1), ray.view(-1, 1, 3)) / torch.bmm(ray.view(-1, 1, 3), ray.view(-1, 3, 1))
-            tgt = target_3d.view(-1, 3, 1)
-            px = torch.bmm(proj, tgt) / diam
-            tgt = tgt / diam
-            k = 50  # 0.02 d
-            per_cell = nn.SmoothL1Loss(reduction="none")(k * px, k * tgt).view(n_cell, -1).mean(dim=1)
-            return per_cell / k
+            if getattr(self, "_kinv", None) is None:
+                # inverse intrinsics once, on the host (the reference calls torch.inverse on the device every step)
+                self._kinv = np.linalg.inv(self.internal_K.detach().cpu().numpy().astype(np.float64)).reshape(-1).tolist()
+            return Reg3dLossFunction.apply(pred_xy, target_3d, self.diameters[cls_labels], self._kinv)
 
         def KDObjectSpaceLoss(self, pred, target_2D, target_3D_in_camera_frame, cls_labels, anchors, pred_t,
                               bbox_trans, weight=None):
@@ -213,7 +206,6 @@ def make_kd_pose_loss(base):
             # only the class logits are flattened (the focal loss reads every cell); the 240-channel regression maps
             # are read in place by the gather/decode kernel at the positive cells -- the reference's flatten of
             # pred_reg (losses/loss.py:62-96) is ~83 MB of copies per direction at batch 64 for ~640 used rows
-            pred_cls_flat = flatten_level_list(pred_cls)
             labels_flat = torch.cat(labels, dim=0)
             aux_3d_flat = torch.cat(aux_3d, dim=0)
             anchors_flat = self._flatten_anchors(anchors)
@@ -227,8 +219,15 @@ def make_kd_pose_loss(base):
             pos_per_img = np.diff(at_ends.cpu().numpy(), prepend=0).tolist()
             total_num_pos = _reduce_sum_int(int(sum(pos_per_img)), labels_flat.device)
 
-            valid_inds = torch.nonzero(labels_flat >= 0).squeeze(1)
-            cls_loss = self.cls_loss_func(pred_cls_flat[valid_inds], labels_flat[valid_inds])
+            f = self.cls_loss_func
+            if all(hasattr(f, a) for a in ("gamma", "alpha", "eps")) and abs(float(f.eps) - 1e-4) < 1e-12 and \
+                    getattr(type(f), "forward", None) is not None and type(f).__name__ in ("SigmoidFocalLoss", "FocalLoss"):
+                # the reference's SigmoidFocalLoss (losses/loss.py:12-40): fused forward + gradient on the per-level
+                # logits, ignored cells (label -1) skipped inside the kernel instead of by boolean-index copies
+                cls_loss = FocalLossFunction.apply(labels_flat, float(f.gamma), float(f.alpha), *pred_cls)
+            else:  # a foreign classification loss: the reference's call (kd_loss.py:133-134)
+                valid_inds = torch.nonzero(labels_flat >= 0).squeeze(1)
+                cls_loss = f(flatten_level_list(pred_cls)[valid_inds], labels_flat[valid_inds])
 
             if pos_inds.numel() > 0:
                 self.pos_per_img = pos_per_img
@@ -238,7 +237,7 @@ def make_kd_pose_loss(base):
                 if self.target_coder.target_type != "3D":
                     raise NotImplementedError("KDPoseLoss: only LOSS_REG_TYPE == '3D' carries the KD loss (kd_loss.py:150-153)")
                 if self.weighted_ot:
-                    self.pred_cls = torch.clamp(torch.sigmoid(pred_cls_flat[pos_inds]), min=10e-4, max=1 - 10e-4)
+                    self.pred_cls = torch.clamp(torch.sigmoid(flatten_level_list(pred_cls)[pos_inds]), min=10e-4, max=1 - 10e-4)
                 if getattr(self.target_coder, "regression_type", "POINT") != "POINT":
                     raise NotImplementedError("KDPoseLoss: only the 'POINT' regression type is defined (models/model.py:145,163)")
                 self.cls_id = torch.unique(cls_label)

@@ -284,3 +284,92 @@ class GatherDecodeFunction(torch.autograd.Function):
 def gather_decode(pred_reg, pos_inds, cls_label, anchors_pos, bbox_trans_pos=None):
     """Decoded ``(npos*8, 2)`` pixel key-points of the positive cells, gathered from the per-level head outputs."""
     return GatherDecodeFunction.apply(pos_inds, cls_label, anchors_pos.contiguous(), bbox_trans_pos, *pred_reg)
+
+
+_focal_ws = {}
+
+
+def _focal_workspace(dev):
+    buf = _focal_ws.get(dev.index)
+    if buf is None:
+        buf = torch.zeros(int(_lib.lib().kdot_focal_workspace_bytes()), dtype=torch.uint8, device=dev)  # ticket starts at 0
+        _focal_ws[dev.index] = buf
+    return buf
+
+
+class FocalLossFunction(torch.autograd.Function):
+    """``SigmoidFocalLoss`` (reference ``losses/loss.py:12-40``) over every non-ignored (cell, class) pair, forward and
+    gradient in ONE launch on the per-level ``(nimg, C, H, W)`` logits as the head produced them
+    (``kdot_focal_loss_fwd_bwd``): no flatten of the class maps, no boolean-index copies of ``pred_cls_flatten[valid]``.
+
+    ``apply(labels_flat, gamma, alpha, *pred_cls) -> 0-dim loss``; ``labels_flat (nimg * cells,) int64`` in the reference's
+    label order."""
+
+    @staticmethod
+    def forward(ctx, labels_flat, gamma, alpha, *pred_cls):
+        L = _lib.lib()
+        levels = [c.detach() if c.is_contiguous() else c.detach().contiguous() for c in pred_cls]
+        for c in levels:
+            _check_f32_cuda("pred_cls level", c)
+        nimg, ncls = levels[0].shape[0], levels[0].shape[1]
+        dev = levels[0].device
+        cells = sum(int(c.shape[2] * c.shape[3]) for c in levels)
+        labels_flat = labels_flat.to(torch.int64).contiguous()
+        if labels_flat.numel() != nimg * cells:
+            raise ValueError("labels do not cover nimg * cells")
+        need_grad = any(c.requires_grad for c in pred_cls)
+        sizes = [c.numel() for c in levels]
+        flat = torch.empty(sum(sizes) if need_grad else 0, dtype=torch.float32, device=dev)
+        grads, o = [], 0
+        for c, n in zip(levels, sizes):
+            grads.append(flat[o:o + n].view(c.shape) if need_grad else None)
+            o += n
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        nl = len(levels)
+        hw = (C.c_int32 * nl)(*[int(c.shape[2] * c.shape[3]) for c in levels])
+        ptrs = (C.c_void_p * nl)(*[c.data_ptr() for c in levels])
+        gptrs = (C.c_void_p * nl)(*[g.data_ptr() for g in grads]) if need_grad else None
+        wsp = _focal_workspace(dev)
+        with _on_device(dev):
+            rc = L.kdot_focal_loss_fwd_bwd(ptrs, hw, nl, nimg, ncls, labels_flat.data_ptr(), float(gamma), float(alpha),
+                                           loss.data_ptr(), gptrs, wsp.data_ptr(), wsp.numel(),
+                                           torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "kdot_focal_loss_fwd_bwd")
+        ctx.grads = grads
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None, None, None, *[None if gr is None else gr * g for gr in ctx.grads])
+
+
+class Reg3dLossFunction(torch.autograd.Function):
+    """The 3-D object-space regression loss of ``losses/kd_loss.py:57-71`` on decoded key-points, forward and
+    ``d/d(key-points)`` in one launch (``kdot_reg3d_loss_fwd_bwd``).  ``apply(pred_xy (n*8, 2), target_3d (n, 8, 3),
+    diam_cell (n,), kinv (9 floats, host)) -> per-cell losses (n,)``."""
+
+    @staticmethod
+    def forward(ctx, pred_xy, target_3d, diam_cell, kinv):
+        L = _lib.lib()
+        xy = pred_xy.detach().contiguous()
+        tgt = target_3d.detach().to(torch.float32).contiguous()
+        diam = diam_cell.detach().to(torch.float32).contiguous()
+        _check_f32_cuda("pred_xy", xy)
+        n = diam.numel()
+        if xy.shape != (n * 8, 2) or tgt.numel() != n * 24:
+            raise ValueError("pred_xy must be (n*8, 2) and target_3d (n, 8, 3)")
+        dev = xy.device
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        g_xy = torch.empty_like(xy)
+        k9 = (C.c_float * 9)(*[float(v) for v in kinv])
+        with _on_device(dev):
+            rc = L.kdot_reg3d_loss_fwd_bwd(xy.data_ptr(), tgt.data_ptr(), diam.data_ptr(), k9, n, out.data_ptr(),
+                                           g_xy.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "kdot_reg3d_loss_fwd_bwd")
+        ctx.save_for_backward(g_xy)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (g_xy,) = ctx.saved_tensors
+        return g_xy * g.repeat_interleave(8).view(-1, 1), None, None, None
