@@ -209,6 +209,34 @@ size_t kdot_focal_workspace_bytes(void);
 int kdot_reg3d_loss_fwd_bwd(const float* xy, const float* target3d, const float* diam_cell, const float* kinv9_host,
                             int npos, float* loss_cell, float* g_xy, void* cuda_stream);
 
+/*
+ * Device-side SSC positive sampling: the label assignment of PoseLossDzi.prepare_targets (losses/loss.py:164-268,
+ * POSITIVE_TYPE == 'SSC').  All images in one launch per stage.
+ *
+ * kdot_ssc_count: mask[nimg][mh][mw] object-index maps (0 background, g + 1 object g: PoseAnnot.mask), anchors[cells][4]
+ * of ONE image (xyxy, level-major), hw_lvl / size_lvl host arrays, per-image objects padded to maxgt (<= 8):
+ * num_gt[nimg], rot[nimg][maxgt][3][3], trans[nimg][maxgt][3], kp3d[nimg][maxgt][8][3] (key-points of the object's class),
+ * K[nimg][3][3], bbox_trans[nimg][2][3] or NULL.  Outputs: gtid[nimg][cells] (owner of every anchor centre, loss.py:194-203),
+ * span[nimg][maxgt] (box_span of the reprojected 3-D box, libs/poses.py:280-300 + libs/boxlist.py:229-233),
+ * nk[nimg][nlvl][maxgt] (per-level budget, loss.py:207-215), count[nimg][nlvl][maxgt] (candidates, loss.py:224).
+ *
+ * kdot_ssc_pick: picks[nimg][nlvl][maxgt][cap] = a uniform draw without replacement of min(nk, count) ordinals in
+ * [0, count) from a counter-based generator keyed by `seed` (-1 pads) -- the device replacement of loss.py:227's CPU
+ * torch.randperm.  For bit-exact parity with a reference run the caller fills `picks` on the host instead
+ * (torch.randperm(count)[:k] in the reference's image / level / object order).
+ *
+ * kdot_ssc_assign: labels[nimg][cells] int64 (class + 1 drawn, -1 in mask but not drawn, 0 background: loss.py:236-252),
+ * owner[nimg][cells] (anchors_to_gt_indexs), npos[nimg].  cls_plus1[nimg][maxgt] = class_ids + 1.
+ */
+int kdot_ssc_count(const float* mask, int mh, int mw, const float* anchors, const int32_t* hw_lvl, const float* size_lvl,
+                   int nlvl, int nimg, int maxgt, const int32_t* num_gt, const float* rot, const float* trans,
+                   const float* kp3d, const float* K, const float* bbox_trans, int positive_num, float positive_lambda,
+                   uint8_t* gtid, int32_t* count, int32_t* nk, float* span, void* cuda_stream);
+int kdot_ssc_pick(const int32_t* count, const int32_t* nk, int nimg, int nlvl, int maxgt, int cap, uint64_t seed,
+                  int32_t* picks, void* cuda_stream);
+int kdot_ssc_assign(const uint8_t* gtid, const int32_t* picks, const int64_t* cls_plus1, const int32_t* hw_lvl, int nlvl,
+                    int nimg, int maxgt, int cap, int64_t* labels, int32_t* owner, int32_t* npos, void* cuda_stream);
+
 /* Diagnostics */
 const char* kdot_last_error(void);
 int kdot_version(void);

@@ -21,6 +21,7 @@ EXPORTS = (
     "kdot_sinkhorn_fwd_bwd_host", "kdot_host_ctx_last_traffic", "kdot_host_ctx_last_timing", "kdot_select_cells", "kdot_gather_decode_fwd", "kdot_gather_decode_bwd", "kdot_last_error",
     "kdot_version", "kdot_launch_count", "kdot_measure_fp32_peak_tflops", "kdot_debug_set_clock_buffer",
     "kdot_focal_loss_fwd_bwd", "kdot_focal_workspace_bytes", "kdot_reg3d_loss_fwd_bwd",
+    "kdot_ssc_count", "kdot_ssc_pick", "kdot_ssc_assign",
 )
 
 _lib = None
@@ -74,6 +75,12 @@ def load(path: str):
     L.kdot_focal_workspace_bytes.argtypes = []
     L.kdot_reg3d_loss_fwd_bwd.restype = i32
     L.kdot_reg3d_loss_fwd_bwd.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
+    L.kdot_ssc_count.restype = i32
+    L.kdot_ssc_count.argtypes = [vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, f32, vp, vp, vp, vp, vp]
+    L.kdot_ssc_pick.restype = i32
+    L.kdot_ssc_pick.argtypes = [vp, vp, i32, i32, i32, i32, C.c_uint64, vp, vp]
+    L.kdot_ssc_assign.restype = i32
+    L.kdot_ssc_assign.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     L.kdot_measure_fp32_peak_tflops.restype = C.c_double
     L.kdot_measure_fp32_peak_tflops.argtypes = [i32, i32]
     return L

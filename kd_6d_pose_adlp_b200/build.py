@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libkdot.so")
 # test-only A/B build of the same ABI: the streaming kernel evaluates every column tile (no exact tile skipping)
 NOSKIP_LIB_PATH = os.path.join(LIB_DIR, "libkdot_noskip.so")
 STAMP = os.path.join(LIB_DIR, "libkdot.stamp")
-SOURCES = ["kdot_api.cu", "kdot_small.cu", "kdot_tiled.cu", "kdot_stream.cu", "kdot_mmd.cu", "kdot_select.cu", "kdot_decode.cu", "kdot_losses.cu"]
+SOURCES = ["kdot_api.cu", "kdot_small.cu", "kdot_tiled.cu", "kdot_stream.cu", "kdot_mmd.cu", "kdot_select.cu", "kdot_decode.cu", "kdot_losses.cu", "kdot_targets.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v",

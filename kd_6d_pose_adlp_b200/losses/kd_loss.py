@@ -196,8 +196,52 @@ def make_kd_pose_loss(base):
             if pending is not None:
                 _status_error(pending.cpu().tolist(), "KDPoseLoss (previous step)")
 
+        def _call_with_device_targets(self, pred_cls, pred_reg, targets, anchors, pred_t, mode):
+            """``__call__`` with the SSC label assignment on the device (``kd_6d_pose_adlp_b200.targets``) instead of
+            the base class' host loops (``losses/loss.py:164-268``): same three losses, same instance attributes."""
+            from ..targets import positives_aux, ssc_assign
+
+            if self.positive_type != "SSC":
+                raise NotImplementedError("DEVICE_TARGETS implements POSITIVE_TYPE == 'SSC' (the only type the reference defines)")
+            self.batch_size = len(targets)
+            self.h, self.w = 480, 640
+            first = anchors[0]
+            anchors_one = torch.cat([a.bbox if hasattr(a, "bbox") else a for a in first], dim=0)
+            hw = [int(c.shape[2] * c.shape[3]) for c in pred_cls]
+            self._ssc_step = getattr(self, "_ssc_step", 0) + 1
+            res = ssc_assign(targets, anchors_one, hw, self.anchor_sizes, self.positive_num, self.positive_lambda, mode=mode,
+                             seed=int(os.environ.get("KDOT_SSC_SEED", "0")) * 1000003 + self._ssc_step)
+            labels_flat = res["labels"]
+            f = self.cls_loss_func
+            cls_loss = FocalLossFunction.apply(labels_flat, float(f.gamma), float(f.alpha), *pred_cls)
+            pos_inds = torch.nonzero(labels_flat > 0).squeeze(1)
+            pos_per_img = res["npos"].cpu().tolist()          # the one host sync of the step
+            total_num_pos = _reduce_sum_int(int(sum(pos_per_img)), labels_flat.device)
+            if pos_inds.numel() > 0:
+                self.pos_per_img = pos_per_img
+                if _num_gpus() <= 1:
+                    assert sum(self.pos_per_img) == total_num_pos
+                if self.target_coder.target_type != "3D":
+                    raise NotImplementedError("KDPoseLoss: only LOSS_REG_TYPE == '3D' carries the KD loss (kd_loss.py:150-153)")
+                cls_label, aux_3d_pos, bt_pos = positives_aux(res, pos_inds)
+                if self.weighted_ot:
+                    self.pred_cls = torch.clamp(torch.sigmoid(flatten_level_list(pred_cls)[pos_inds]), min=10e-4, max=1 - 10e-4)
+                self.cls_id = torch.unique(cls_label)
+                cell = pos_inds - torch.div(pos_inds, res["cells"], rounding_mode="floor") * res["cells"]
+                pred_xy = gather_decode(pred_reg, pos_inds, cls_label, anchors_one[cell], bt_pos)
+                reg_loss, kd_loss = self._losses_from_keypoints(pred_xy, aux_3d_pos, cls_label, pred_t)
+            else:
+                reg_loss = sum(r.sum() for r in pred_reg)
+                kd_loss = reg_loss
+            if hasattr(self, "step"):
+                self.step += 1
+            return [cls_loss, reg_loss, kd_loss]
+
         def __call__(self, pred_cls, pred_reg, targets, anchors, pred_t):
             self.check_status()
+            mode = (getattr(self, "cfg_kd", None) or {}).get("DEVICE_TARGETS") or os.environ.get("KDOT_DEVICE_TARGETS")
+            if mode:
+                return self._call_with_device_targets(pred_cls, pred_reg, targets, anchors, pred_t, mode)
             labels, reg_targets, aux_raw_boxes, aux_3d, aux_bbox_trans = self.prepare_targets(targets, anchors)
             self.batch_size = len(labels)
             self.h = 480  # full-image size, not the 256 crop (kd_loss.py:116-117)
