@@ -29,34 +29,42 @@ MAX_GT = 8
 
 
 def _stack_targets(targets, dev):
-    """Per-image object lists padded to ``maxgt`` (<= 8) and stacked: six small tensors for the whole mini-batch."""
+    """Per-image object lists padded to ``maxgt`` (<= 8) and stacked -- a dozen launches for the whole mini-batch (one
+    ``cat`` / ``stack`` per field and one scatter into the padded layout), independent of the number of images."""
     nimg = len(targets)
     ngt = [int(t.class_ids.shape[0]) for t in targets]
     maxgt = max(1, max(ngt))
     if maxgt > MAX_GT:
         raise ValueError(f"kdot_ssc_count handles up to {MAX_GT} objects per image, got {maxgt}")
     f32 = dict(dtype=torch.float32, device=dev)
+    with_obj = [t for t, g in zip(targets, ngt) if g > 0]
     rot = torch.zeros(nimg, maxgt, 3, 3, **f32)
     trans = torch.zeros(nimg, maxgt, 3, **f32)
     kp3d = torch.zeros(nimg, maxgt, 8, 3, **f32)
     cls1 = torch.zeros(nimg, maxgt, dtype=torch.int64, device=dev)
-    for i, t in enumerate(targets):
-        g = ngt[i]
-        if g == 0:
-            continue
-        ids = t.class_ids.to(dev).long()
-        rot[i, :g] = t.rotations.to(**f32).view(g, 3, 3)
-        trans[i, :g] = t.translations.to(**f32).view(g, 3)
-        kp3d[i, :g] = t.keypoints_3d.to(**f32)[ids]
-        cls1[i, :g] = ids + 1
-    mask = torch.stack([t.mask.to(**f32) for t in targets])
-    K = torch.stack([t.K.to(**f32).view(3, 3) for t in targets])
+    if with_obj:
+        ids = torch.cat([t.class_ids.reshape(-1) for t in with_obj]).to(dev).long()
+        rflat = torch.cat([t.rotations.reshape(-1, 3, 3) for t in with_obj]).to(**f32)
+        tflat = torch.cat([t.translations.reshape(-1, 3) for t in with_obj]).to(**f32)
+        shared = all(t.keypoints_3d is with_obj[0].keypoints_3d for t in with_obj)
+        if shared:
+            kflat = with_obj[0].keypoints_3d.to(**f32)[ids]
+        else:
+            kflat = torch.cat([t.keypoints_3d.to(**f32)[t.class_ids.to(dev).long()] for t in with_obj])
+        where = np.asarray([(i, g) for i, n in enumerate(ngt) for g in range(n)], np.int64)
+        idx = torch.from_numpy(where).to(dev, non_blocking=True)
+        ii, gg = idx[:, 0], idx[:, 1]
+        rot[ii, gg], trans[ii, gg], kp3d[ii, gg], cls1[ii, gg] = rflat, tflat, kflat, ids + 1
+    mask = torch.stack([t.mask for t in targets]).to(**f32)
+    same_k = all(t.K is targets[0].K for t in targets)
+    K = (targets[0].K.to(**f32).view(1, 3, 3).expand(nimg, 3, 3).contiguous() if same_k
+         else torch.stack([t.K.reshape(3, 3) for t in targets]).to(**f32))
     has_bt = [getattr(t, "bbox_trans", None) is not None for t in targets]
     if any(has_bt) and not all(has_bt):
         raise ValueError("either every target carries bbox_trans or none does")
-    bt = torch.stack([t.bbox_trans.to(**f32).view(2, 3) for t in targets]) if all(has_bt) else None
+    bt = torch.stack([t.bbox_trans.reshape(2, 3) for t in targets]).to(**f32) if all(has_bt) else None
     return dict(nimg=nimg, ngt=ngt, maxgt=maxgt, rot=rot, trans=trans, kp3d=kp3d, cls1=cls1, mask=mask.contiguous(), K=K, bt=bt,
-                num_gt=torch.tensor(ngt, dtype=torch.int32, device=dev))
+                num_gt=torch.tensor(ngt, dtype=torch.int32).to(dev, non_blocking=True))
 
 
 def ssc_assign(targets, anchors_one_image: torch.Tensor, level_hw: Sequence[int], anchor_sizes: Sequence[float],

@@ -91,11 +91,73 @@ def main():
             out.append((time.perf_counter() - t0) * 1e3)
         return statistics.median(out)
 
+    # ---- REAL (not replayed) target assignment on the device: cfg_kd["DEVICE_TARGETS"] = parity | philox ----
+    import types
+
+    arr = scenario.make_target_arrays(nimg, 0)
+    tt = lambda a: torch.tensor(a).to(dev)
+    targets = [types.SimpleNamespace(keypoints_3d=tt(arr["keypoints_3d"]), K=tt(arr["K"]), mask=tt(arr["mask"][i]),
+                                     class_ids=tt(arr["class_ids"][i]), rotations=tt(arr["rotations"][i]),
+                                     translations=tt(arr["translations"][i]), bbox_trans=tt(arr["bbox_trans"][i])) for i in range(nimg)]
+    h_cls, h_reg = scenario.make_head_outputs(nimg, HW, 200, teacher=False, target_seed=0)
+    d_cls = [torch.from_numpy(a).to(dev).requires_grad_(True) for a in h_cls]
+    d_reg = [torch.from_numpy(a).to(dev).requires_grad_(True) for a in h_reg]
+
+    def make_real(mode):
+        fn = KDPoseLoss(2.0, 0.25, scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES, "SSC", 10, 1.0, 9,
+                        scenario.INTERNAL_K, scenario.MESH_DIAMETERS,
+                        TargetCoder("POINT", scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES, target_type="3D"),
+                        dict(scenario.CFG_KD, DEVICE_TARGETS=mode))
+
+        def run():
+            for t in d_cls + d_reg:
+                t.grad = None
+            c, r, k = fn(d_cls, d_reg, targets, anchors, teacher())
+            (0.1 * c + r + 5.0 * k).backward()
+            return float(k.detach())
+        return run
+
+    real = {m: timed(make_real(m)) for m in ("parity", "philox")}
+    ref_ms = None
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref_root, "losses")):
+        # the reference's own KDPoseLoss (its prepare_targets loops + the restated geomloss as stock torch ops) on the same GPU
+        os.environ["KDOT_REFERENCE_ROOT"] = ref_root
+        from oracle import ref_loader
+
+        ref_loader.REFERENCE_ROOT = ref_root
+        ref = ref_loader.load()
+        r_targets = [ref.PoseAnnot(torch.tensor(arr["keypoints_3d"]), torch.tensor(arr["K"]), torch.tensor(arr["mask"][i]),
+                                   torch.tensor(arr["class_ids"][i]), torch.tensor(arr["rotations"][i]),
+                                   torch.tensor(arr["translations"][i]), 256, 256, bbox_scale=torch.tensor(1.0),
+                                   bbox_trans=torch.tensor(arr["bbox_trans"][i])).to(dev) for i in range(nimg)]
+        gen = ref.modules["model"].make_anchor_generator_atss(scenario.ANCHOR_SIZES[:4], scenario.ANCHOR_STRIDES[:4]).to(dev)
+        il = types.SimpleNamespace(sizes=[(256, 256)] * nimg, image_sizes=[(256, 256)] * nimg)
+        r_anchors = gen(il, [torch.zeros(nimg, 1, h, w, device=dev) for h, w in HW])
+        r_fn = ref.KDPoseLoss(2.0, 0.25, scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES, "SSC", 10, 1.0, 9, scenario.INTERNAL_K,
+                              scenario.MESH_DIAMETERS, ref.TargetCoder("POINT", scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES, target_type="3D"),
+                              dict(scenario.CFG_KD, vis_dir="/tmp/kdot_vis_time"))
+        r_fn.step = 5   # past the step-0 plot
+
+        def run_ref():
+            for t in d_cls + d_reg:
+                t.grad = None
+            c, r, k = r_fn(d_cls, d_reg, r_targets, r_anchors, teacher())
+            (0.1 * c + r + 5.0 * k).backward()
+            return float(k.detach())
+
+        ref_ms = timed(run_ref, warm=2, iters=5)
+
     kf, ku = fused(), unfused()
     rec = {"nimg": nimg, "kd_loss": {"fused": kf, "unfused": ku},
-           "ms_fwd_bwd": {"fused_gather_decode": timed(fused), "flatten_index_decode": timed(unfused)},
+           "ms_fwd_bwd": {"replayed_targets_fused": timed(fused), "replayed_targets_flatten_index_decode": timed(unfused),
+                          "device_targets_parity": real["parity"], "device_targets_philox": real["philox"],
+                          "reference_KDPoseLoss_on_this_gpu": ref_ms},
+           "note": "forward + backward of [cls, reg, kd] through seam B0, batch %d; 'device_targets_*' include the REAL SSC label "
+                   "assignment (kdot_ssc_*), 'reference' is the reference's own KDPoseLoss (host-loop prepare_targets, restated geomloss "
+                   "as stock torch ops) on the same GPU" % nimg,
            "gpu": torch.cuda.get_device_name(0)}
-    rec["speedup"] = rec["ms_fwd_bwd"]["flatten_index_decode"] / rec["ms_fwd_bwd"]["fused_gather_decode"]
+    rec["speedup_vs_reference"] = None if ref_ms is None else ref_ms / real["philox"]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "kd_pose_loss_timing.json"), "w") as fh:
         json.dump(rec, fh, indent=1)
