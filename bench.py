@@ -450,6 +450,89 @@ def allreduce_leg(dev, bench, barrier, max_over_ranks, world, rank):
     return out
 
 
+def b0_and_select_legs(dev, nimg=64):
+    """The callers either side of the kernel, through the reference-facing Python seams:
+    KDPoseLoss.__call__ + backward with the REAL SSC target assignment on the device, and PostProcessorKD's selection
+    kernel.  Host wall clock around a synchronised call (these paths are launch / host bound), median of 20."""
+    import types
+
+    import torch
+
+    from kd_6d_pose_adlp_b200.losses.kd_loss import make_kd_pose_loss
+    from kd_6d_pose_adlp_b200.postprocess.postprocess_kd import select_cells
+    from kd_6d_pose_adlp_b200.target_coder import TargetCoder, grid_anchors
+    from tests import doubles, scenario
+
+    def timed(fn, warm=5, iters=20):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(iters):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize(dev)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        return statistics.median(ts)
+
+    s_hw = [(32, 32), (16, 16), (8, 8), (4, 4)]
+    t_hw = s_hw + [(2, 2)]
+    arr = scenario.make_target_arrays(nimg, 0)
+    tt = lambda a: torch.tensor(a).to(dev)
+    targets = [types.SimpleNamespace(keypoints_3d=tt(arr["keypoints_3d"]), K=tt(arr["K"]), mask=tt(arr["mask"][i]),
+                                     class_ids=tt(arr["class_ids"][i]), rotations=tt(arr["rotations"][i]),
+                                     translations=tt(arr["translations"][i]), bbox_trans=tt(arr["bbox_trans"][i])) for i in range(nimg)]
+    s_cls, s_reg = scenario.make_head_outputs(nimg, s_hw, 200, teacher=False, target_seed=0)
+    t_cls, t_reg = scenario.make_head_outputs(nimg, t_hw, 100, teacher=True, target_seed=0)
+    d_cls = [torch.from_numpy(a).to(dev).requires_grad_(True) for a in s_cls]
+    d_reg = [torch.from_numpy(a).to(dev).requires_grad_(True) for a in s_reg]
+    tc = [torch.from_numpy(a).to(dev) for a in t_cls]
+    tr = [torch.from_numpy(a).to(dev) for a in t_reg]
+    sel = select_cells(tc, tr, scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES, 0.1, 10, 1.0)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sel_us = []
+    for _ in range(25):
+        e0.record()
+        select_cells(tc, tr, scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES, 0.1, 10, 1.0)
+        e1.record()
+        e1.synchronize()
+        sel_us.append(e0.elapsed_time(e1) * 1e3)
+    sel_us = statistics.median(sel_us[5:])
+    logit_bytes = sum(a.size for a in t_cls) * 4
+    peaks, _src = measured_peaks()
+    # teacher dict for the loss from the selection itself (level-0 cells of class 0; PnP is host work outside this leg)
+    cnt = sel["sel_count"].view(nimg, -1)[:, 0].cpu().tolist()
+    kp = sel["sel_kpts"].view(nimg, -1, sel["cap"], 16)[:, 0]
+    sc = sel["sel_score"].view(nimg, -1, sel["cap"])[:, 0]
+    kp2d = torch.cat([kp[i, :cnt[i]].view(-1, 2, 8).transpose(1, 2) for i in range(nimg)]).contiguous()
+    kcls = torch.cat([sc[i, :cnt[i]].view(-1, 1).repeat(1, 8) for i in range(nimg)]).contiguous()
+    KDPoseLoss = make_kd_pose_loss(doubles.ReplayBase)
+    lv = grid_anchors(s_hw, scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES, device=dev)
+    anchors = [lv for _ in range(nimg)]
+    out = {"images": nimg, "unit": "ms per forward+backward of [cls, reg, kd] through KDPoseLoss.__call__ (seam B0), host wall clock"}
+    for mode in ("philox", "parity"):
+        fn = KDPoseLoss(2.0, 0.25, scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES, "SSC", 10, 1.0, 9, scenario.INTERNAL_K,
+                        scenario.MESH_DIAMETERS, TargetCoder("POINT", scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES, target_type="3D"),
+                        dict(scenario.CFG_KD, DEVICE_TARGETS=mode))
+
+        def run():
+            for t in d_cls + d_reg:
+                t.grad = None
+            c, r, k = fn(d_cls, d_reg, targets, anchors, {"post_kp_2d": kp2d.clone(), "post_kp_cls": kcls, "post_pos_per_img": cnt})
+            (0.1 * c + r + 5.0 * k).backward()
+
+        out[f"device_targets_{mode}_ms"] = timed(run)
+    out["images_per_s_philox"] = nimg / (out["device_targets_philox_ms"] * 1e-3)
+    out["note"] = ("real (not replayed) SSC target assignment on the device; the reference's own KDPoseLoss on the same GPU takes "
+                   "~530 ms for this batch (tools/time_kd_pose_loss.py, profiles/r02_kd_pose_loss_timing.json)")
+    select = {"kernel": "kdot_select_kernel", "images": nimg, "us": sel_us, "logit_bytes": logit_bytes,
+              "GBps": logit_bytes / sel_us / 1e3, "hbm_peak_GBps": peaks.get("hbm_gbs"),
+              "frac_of_hbm": logit_bytes / sel_us / 1e3 / peaks.get("hbm_gbs", 6552.0),
+              "note": "one streaming pass over nimg x cells x 15 teacher logits is the bound; the launch is latency-bound at this size"}
+    return out, select
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -462,6 +545,7 @@ def main():
     ap.add_argument("--blur", type=float, default=None, help="override the blur (final temperature = blur**p)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the secondary dense-workload roofline leg")
+    ap.add_argument("--no-b0", action="store_true", help="skip the KDPoseLoss.__call__ / selection-kernel legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -584,6 +668,12 @@ def main():
 
     if world > 1:
         line["allreduce"] = allreduce_leg(dev, bench, barrier, max_over_ranks, world, rank)
+
+    if rank == 0 and world == 1 and not args.no_b0 and args.workload == "ape_b64":
+        try:
+            line["e2e_b0"], line["select"] = b0_and_select_legs(dev)
+        except Exception as exc:  # these legs import tests/scenario.py (synthetic head outputs); never fail the headline for them
+            line["e2e_b0"] = {"unavailable": repr(exc)}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = batch if WORKLOADS[args.workload]["dense"] is None else make_batch(args.workload, 0, nimg=1)

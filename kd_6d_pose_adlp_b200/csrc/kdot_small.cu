@@ -111,6 +111,19 @@ __device__ __forceinline__ void fast_max(const float* __restrict__ cx, const flo
   }
 }
 
+// Offsets beyond ~1e6 log2-units (un-normalised pixel coordinates at blur = 1e-3): the fp32 estimate of the row maximum
+// is no longer good to +-2, the maxima are taken in float64.  Rare and slow (fmax on doubles): kept out of line so that it
+// does not weigh on the register allocation and scheduling of the rounds.
+static __device__ __noinline__ void hi_reference_f64(const double* d2s, const double* hd, int ncol, int ncolx, double coef,
+                                                     double& refX, double& refY) {
+  double mx = -1.0e300, my = -1.0e300;
+  for (int j = 0; j < ncol; ++j) {
+    const double t = fma(coef, d2s[j * 32], hd[j]);
+    if (j < ncolx) mx = fmax(mx, t); else my = fmax(my, t);
+  }
+  refX = mx + 2.0; refY = my + 2.0;
+}
+
 // d2s: this lane's squared distances to every column in float64, [column][lane] in shared memory (computed once per
 // (image, slot): they do not change between rounds), so a pair costs one LDS.64, one DADD and one DFMA on the DP pipe,
 // three integer operations for the re-packing and the one ex2.
@@ -120,16 +133,7 @@ __device__ __forceinline__ RoundOut<CH, GRAD> hi_round(const double* __restrict_
                                                        int nchx, float pxf, float pyf, double coef, float mX, float mY,
                                                        float hmag) {
   double refX = (double)mX + 2.0, refY = (double)mY + 2.0;
-  if ((hmag + fabsf(mX) + fabsf(mY)) * 9.5e-7f > 1.0f) {
-    // offsets beyond ~1e6 log2-units (un-normalised pixel coordinates at blur = 1e-3): the fp32 estimate of the row
-    // maximum is no longer good to +-2, take the maxima in float64 (rare, slow: fmax on doubles)
-    double mx = -1.0e300, my = -1.0e300;
-    for (int j = 0; j < 4 * CH; ++j) {
-      const double t = fma(coef, d2s[j * 32], hd[j]);
-      if (j < 4 * nchx) mx = fmax(mx, t); else my = fmax(my, t);
-    }
-    refX = mx + 2.0; refY = my + 2.0;
-  }
+  if ((hmag + fabsf(mX) + fabsf(mY)) * 9.5e-7f > 1.0f) hi_reference_f64(d2s, hd, 4 * CH, 4 * nchx, coef, refX, refY);
   float sX = 0.f, sY = 0.f, gXx = 0.f, gXy = 0.f, gYx = 0.f, gYy = 0.f;
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
@@ -164,6 +168,7 @@ struct FastCtx {
   double* hbd;   // float64 copy of hb (high-precision rounds)
   double* d2s;   // [40 columns][32 lanes] float64 squared distances of this lane's point to every column
   int nchx;                         // student chunks (padded student columns / 4)
+  int nstu;                         // student points N: lanes [0, N) are student rows, [N, N + M) teacher rows
   bool act, isx;
   int col;                          // padded column slot of this lane's point
   float px, py, wgt, lw2;
@@ -181,6 +186,7 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
   const float eps0 = (float)is.eps0;
   double potS = 0.0, potC = 0.0;
   float hmag = 0.f;  // max |h| over this slot's columns, as published for the current round (hi_mag_factor test)
+  double addX = 0.0, addY = 0.0;  // centres of the consumed student / teacher column offsets (0 in the init round)
   int cur = 0;
   for (int r = 0; r < nrounds - 1; ++r) {
     if (r >= 32 && (r & 31) == 0)  // schedules longer than 32 rounds: next block of constants
@@ -190,6 +196,16 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
     double lseX, lseY;
     const float coef = __shfl_sync(0xffffffffu, mine.coef, r & 31);
     const float eps = __shfl_sync(0xffffffffu, mine.eps, r & 31);
+    // centres for the h this round publishes (potentials as they stand after round r - 1; 0 before the first update)
+#ifndef KDOT_SMALL_NO_CENTRE
+    const double pSX = __shfl_sync(0xffffffffu, potS, 0), pSY = __shfl_sync(0xffffffffu, potS, c.nstu);
+    const double pCX = __shfl_sync(0xffffffffu, potC, 0), pCY = __shfl_sync(0xffffffffu, potC, c.nstu);
+#else
+    const double pSX = 0.0, pSY = 0.0, pCX = 0.0, pCY = 0.0;
+#endif
+    const double ownS = c.isx ? pSX : pSY, ownC = c.isx ? pCX : pCY;   // this lane's column: which set it belongs to
+    const double refX = c.isx ? pSX : pCX;   // student columns: student rows read h^S[X], teacher rows h^C[X]
+    const double refY = c.isx ? pCY : pSY;   // teacher columns: student rows read h^C[Y], teacher rows h^S[Y]
     const float* hp = c.hb + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
     if (!(is_hi_round(r, nrounds, eps, eps0) && hmag * hi_mag_factor(r, nrounds) > 1.0f)) {
       const RoundOut<CH, false> o = fast_round<CH, false>(c.cx, c.cy, hp, c.nchx, c.px, c.py, coef);
@@ -202,13 +218,22 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
       const RoundOut<CH, false> o = hi_round<CH, false>(c.d2s, hpd, c.cx, c.cy, c.nchx, c.px, c.py, coefd, mX, mY, hmag);
       lseX = o.lseX; lseY = o.lseY;
     }
+    lseX += addX; lseY += addY;   // the centres the consumed h was published relative to (see below)
     const double nS = scaled * (c.isx ? lseX : lseY);
     const double nC = scaled * (c.isx ? lseY : lseX);
     potS = r == 0 ? nS : 0.5 * (potS + nS);
     potC = r == 0 ? nC : 0.5 * (potC + nC);
+    // Centred offsets: with unequal total masses every potential of a cloud carries a common term of order
+    // rho * log(mass ratio) / eps (1e4 log2-units at eps = 1e-6) that cancels in h_j - max_j h_j; each of the four
+    // (type S/C, cloud) sets is published relative to the potential its first point had ONE ROUND EARLIER (read at the top
+    // of the round, off the critical path) and the same constant is added
+    // back to the log-sum-exp in float64.  What is left in |h| is the variation across the cloud -- which is what decides
+    // whether fp32 pair arguments are accurate enough (hi_mag_factor).
+    addX = refX * hmuld;
+    addY = refY * hmuld;
     hmag = 0.f;
     if (c.act) {
-      const double hS = fma(potS, hmuld, c.lw2d), hC = fma(potC, hmuld, c.lw2d);
+      const double hS = fma(potS - ownS, hmuld, c.lw2d), hC = fma(potC - ownC, hmuld, c.lw2d);
       hmag = fmaxf(fabsf((float)hS), fabsf((float)hC));
       float* hn = c.hb + (cur ^ 1) * (2 * kFastMaxCols);
       double* hnd = c.hbd + (cur ^ 1) * (2 * kFastMaxCols);
@@ -218,7 +243,7 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
       hnd[kFastMaxCols + c.col] = c.isx ? hC : hS;
     }
     __syncwarp();
-    hmag = warp_max(hmag);
+    hmag = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(hmag)));  // non-negative floats order like their bits
     cur ^= 1;
   }
   const int r = nrounds - 1;
@@ -246,6 +271,7 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
     lseX = o.lseX; lseY = o.lseY; sX = o.sX; sY = o.sY;
     gXx = o.gXx; gXy = o.gXy; gYx = o.gYx; gYy = o.gYy;
   }
+  lseX += addX; lseY += addY;
   S_out = rc_last.scaled * (c.isx ? lseX : lseY);
   C_out = rc_last.scaled * (c.isx ? lseY : lseX);
   // barycentric displacements  sum_j W_ij (p_j - p_i)  against own / other cloud (student rows use them)
@@ -289,6 +315,7 @@ __global__ void __launch_bounds__(256, KDOT_SMALL_MINBLOCKS) kdot_small_fast_ker
   c.cx = wbase_s; c.cy = wbase_s + kFastMaxCols; c.hb = wbase_s + 2 * kFastMaxCols;
   c.hbd = wbase_d; c.d2s = wbase_d + 4 * kFastMaxCols + lane;
   c.nchx = Nq >> 2;
+  c.nstu = N;
   c.act = lane < P;
   c.isx = lane < N;
   c.col = c.isx ? lane : Nq + (lane - N);

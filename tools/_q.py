@@ -21,5 +21,6 @@ for i in range(3):
 c = clk.cpu().numpy()
 print("image0 N,M", b["pos_per_img"][0], b["pos_per_img_t"][0], "nits", int(nits[0]))
 print("phase stamps img0:", np.diff(c[0, :7]))
-r = c[64:].reshape(-1)[:20]
+r = c[64:66].reshape(-1)[:20]
 print("round stamps:", np.diff(np.concatenate([[c[0, 4]], r[r > 0]])))
+print("hmag x1000:", c[66:68].reshape(-1)[:16])
