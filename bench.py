@@ -493,6 +493,7 @@ def b0_and_select_legs(dev, nimg=64):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sel_us = []
     for _ in range(25):
+        torch.cuda._sleep(400000)   # GPU-side delay: the host enqueues <e0, kernel, e1> before the GPU reaches e0
         e0.record()
         select_cells(tc, tr, scenario.ANCHOR_SIZES, scenario.ANCHOR_STRIDES, 0.1, 10, 1.0)
         e1.record()

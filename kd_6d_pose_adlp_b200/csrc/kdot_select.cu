@@ -73,6 +73,16 @@ __device__ __forceinline__ void decode_cell(const SelectParams& p, int img, int 
   }
 }
 
+// same, one offset channel per thread (threads 0..15 of the CTA): the 16 strided loads of a cell are in flight together
+__device__ __forceinline__ void decode_cell_par(const SelectParams& p, int img, int cls, int l, int loc, float* out16, int k) {
+  const int hw = p.hw[l], wd = p.wd[l];
+  const float size = p.sizes[l], stride = p.stride[l];
+  const int hy = loc / wd, wx = loc - hy * wd;
+  const float ac = __fadd_rn(__fmul_rn((float)(k < 8 ? wx : hy), stride), 0.5f * stride);
+  const float* base = p.reg[l] + ((size_t)img * p.C * 16 + (size_t)cls * 16) * hw + loc;
+  out16[k] = __fadd_rn(__fmul_rn(base[(size_t)k * hw], size), ac);
+}
+
 __global__ void __launch_bounds__(kSelThreads) kdot_select_kernel(SelectParams p) {
   const int q = blockIdx.x;
   const int img = q / p.C, cls = q - img * p.C;
@@ -81,6 +91,7 @@ __global__ void __launch_bounds__(kSelThreads) kdot_select_kernel(SelectParams p
   __shared__ int s_i[kSelThreads / 32];
   __shared__ int s_cnt[kSelMaxLevels];
   __shared__ float s_best16[16];
+  __shared__ int s_pick[64];  // (level << 24) | cell of every selected cell (cap <= 64)
   const float neg = -3.0e38f;
 
   if (threadIdx.x < kSelMaxLevels) s_cnt[threadIdx.x] = 0;
@@ -129,7 +140,7 @@ __global__ void __launch_bounds__(kSelThreads) kdot_select_kernel(SelectParams p
       box_conf = score;
       best_l = l; best_loc = idx;
       __syncthreads();
-      if (threadIdx.x == 0) decode_cell(p, img, cls, l, idx, s_best16);
+      if (threadIdx.x < 16) decode_cell_par(p, img, cls, l, idx, s_best16, threadIdx.x);
       __syncthreads();
       float xmin = s_best16[0], xmax = s_best16[0], ymin = s_best16[8], ymax = s_best16[8];
 #pragma unroll
@@ -177,13 +188,18 @@ __global__ void __launch_bounds__(kSelThreads) kdot_select_kernel(SelectParams p
           p.sel_level[o] = l;
           p.sel_loc[o] = idx;
           p.sel_score[o] = sqrtf(sigmoidf_ref(v));
-          decode_cell(p, img, cls, l, idx, p.sel_kpts + o * 16);
+          s_pick[count] = (l << 24) | idx;
           s_logit[p.off[l] + idx] = neg;  // remove from the pool
         }
         ++count;
       }
       __syncthreads();
     }
+  }
+  // decode of all picked cells at the end: count x 16 independent strided loads spread over the CTA
+  for (int t = threadIdx.x; t < count * 16; t += kSelThreads) {
+    const int k = t >> 4, ch = t & 15, pk = s_pick[k];
+    decode_cell_par(p, img, cls, pk >> 24, pk & 0xffffff, p.sel_kpts + ((size_t)q * p.cap + k) * 16, ch);
   }
   if (threadIdx.x == 0) {
     p.sel_count[q] = count;
@@ -207,7 +223,7 @@ extern "C" int kdot_select_cells(const float* const* cls_lvl, const float* const
   if (!cls_lvl || !reg_lvl || !hw_lvl || !w_lvl || !stride_lvl || !anchor_sizes_all || !sel_count || !sel_level ||
       !sel_loc || !sel_score || !sel_kpts || !nk || !valid_cnt || !best)
     return KDOT_E_BADARG;
-  if (nlvl <= 0 || nlvl > kSelMaxLevels || nsizes < nlvl || nsizes > kSelMaxSizes || nimg < 0 || C <= 0 || cap <= 0)
+  if (nlvl <= 0 || nlvl > kSelMaxLevels || nsizes < nlvl || nsizes > kSelMaxSizes || nimg < 0 || C <= 0 || cap <= 0 || cap > 64)
     return KDOT_E_BADARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return KDOT_E_NODEVICE;
