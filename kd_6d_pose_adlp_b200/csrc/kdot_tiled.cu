@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
   float* hC = hS + 2 * Pq;        // [2][Pq]
   const RoundConst* __restrict__ rcs = prm.sched + (size_t)img * KDOT_MAX_ROUNDS;  // L1/L2-resident, 1 load / round
   __shared__ unsigned int s_ctr[2];
+  __shared__ double s_pref[3][4];     // centres of the published offsets (see kdot_stream.cu: stream_unit), slot r % 3
   __shared__ unsigned int s_hmag[3];  // max |h| (fp32 bits) of the values consumed in round r, slot r % 3 (hi_mag_factor test)
   __shared__ double s_part[kTiledThreads / 32];
 
@@ -364,6 +365,7 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
     hSd[Pq + q] = (double)l2; hCd[Pq + q] = (double)l2;
   }
   if (threadIdx.x == 0) { s_ctr[0] = 0u; s_ctr[1] = 0u; s_hmag[0] = 0u; s_hmag[1] = 0u; s_hmag[2] = 0u; }
+  if (threadIdx.x < 12) s_pref[threadIdx.x >> 2][threadIdx.x & 3] = 0.0;
   __syncthreads();
 
   const int nbx = (N + kUnitRows - 1) / kUnitRows, nby = (M + kUnitRows - 1) / kUnitRows;
@@ -372,6 +374,7 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
   int cur = 0;
   for (int r = 0; r < nrounds - 1; ++r) {
     const RoundConst rc = rcs[r];
+    const double hmul_prev = r > 0 ? rcs[r - 1].hmuld : 0.0;
     const bool hi = is_hi_round(r, nrounds, rc.eps, rcs[0].eps) && __uint_as_float(s_hmag[r % 3]) * hi_mag_factor(r, nrounds) > 1.0f;
     const float* hSc = hS + cur * Pq;
     const float* hCc = hC + cur * Pq;
@@ -394,6 +397,11 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
       const int rbase = rows_x ? 0 : Nq, rcount = rows_x ? N : M;
       const bool cols_x = (rows_x == own);
       const int c0 = cols_x ? 0 : Nq, c1 = cols_x ? Nq : Pq;
+      // centred offsets (the common rho * log(mass ratio) / eps term of a cloud's potentials stays out of the fp32 heads):
+      // consumed h is relative to c_in, published h to p_out; the owner of a set's first row records its new potential
+      // for the h consumed two rounds later (three slots: no reader and writer ever share one within a round)
+      const double c_in = s_pref[r % 3][(own ? 0 : 2) + (cols_x ? 0 : 1)] * hmul_prev;
+      const double p_out = s_pref[(r + 1) % 3][(own ? 0 : 2) + (rows_x ? 0 : 1)];
 
       int ridx[kRows];
       double lse[kRows];
@@ -429,10 +437,11 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
       for (int k = 0; k < kRows; ++k) {
         if (ridx[k] < 0) continue;
         double* pot = own ? potS : potC;
-        const double nv = rc.scaled * lse[k];
+        const double nv = rc.scaled * (lse[k] + c_in);
         const double pv = r == 0 ? nv : 0.5 * (pot[ridx[k]] + nv);
         pot[ridx[k]] = pv;
-        const double hv = fma(pv, rc.hmuld, (double)lw2[ridx[k]]);
+        if (ridx[k] == rbase) s_pref[(r + 2) % 3][(own ? 0 : 2) + (rows_x ? 0 : 1)] = pv;
+        const double hv = fma(pv - p_out, rc.hmuld, (double)lw2[ridx[k]]);
         (own ? hSn : hCn)[ridx[k]] = (float)hv;
         (own ? hSnd : hCnd)[ridx[k]] = hv;
         hm = fmaxf(hm, fabsf((float)hv));
@@ -449,6 +458,9 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
   {
     const int r = nrounds - 1;
     const RoundConst rc = rcs[r];
+    const double hmul_prev = r > 0 ? rcs[r - 1].hmuld : 0.0;
+    const double cSX = s_pref[r % 3][0] * hmul_prev, cSY = s_pref[r % 3][1] * hmul_prev;   // centres of h^S[X], h^S[Y]
+    const double cCX = s_pref[r % 3][2] * hmul_prev, cCY = s_pref[r % 3][3] * hmul_prev;   // centres of h^C[X], h^C[Y]
     const bool hi = is_hi_round(r, nrounds, rc.eps, rcs[0].eps) && __uint_as_float(s_hmag[r % 3]) * hi_mag_factor(r, nrounds) > 1.0f;
     const float* hSc = hS + cur * Pq;
     const float* hCc = hC + cur * Pq;
@@ -487,7 +499,7 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
 #pragma unroll
           for (int k = 0; k < kRows; ++k) {
             const float s = st[k].s.x + st[k].s.y;
-            S[k] = rc.scaled * ((double)st[k].mref + lg2_sum_exact(s));
+            S[k] = rc.scaled * ((double)st[k].mref + lg2_sum_exact(s) + cSX);
             gSx[k] = (st[k].gx.x + st[k].gx.y) / s;
             gSy[k] = (st[k].gy.x + st[k].gy.y) / s;
           }
@@ -496,7 +508,7 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
 #pragma unroll
           for (int k = 0; k < kRows; ++k) {
             const float s = st[k].s.x + st[k].s.y;
-            C[k] = rc.scaled * ((double)st[k].mref + lg2_sum_exact(s));
+            C[k] = rc.scaled * ((double)st[k].mref + lg2_sum_exact(s) + cCY);
             gCx[k] = (st[k].gx.x + st[k].gx.y) / s;
             gCy[k] = (st[k].gy.x + st[k].gy.y) / s;
           }
@@ -508,13 +520,13 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
             rows_reset_hi(sh, cx[src], cy[src]);
             rows_vs_columns_hi<true>(sh, cxd, cyd, hScd, cx, cy, 0, Nq, rc.coefd);
             float s = sh.s.x + sh.s.y;
-            S[k] = rc.scaled * (sh.mref + lg2_sum_exact(s));
+            S[k] = rc.scaled * (sh.mref + lg2_sum_exact(s) + cSX);
             gSx[k] = (sh.gx.x + sh.gx.y) / s;
             gSy[k] = (sh.gy.x + sh.gy.y) / s;
             rows_reset_hi(sh, cx[src], cy[src]);
             rows_vs_columns_hi<true>(sh, cxd, cyd, hCcd, cx, cy, Nq, Pq, rc.coefd);
             s = sh.s.x + sh.s.y;
-            C[k] = rc.scaled * (sh.mref + lg2_sum_exact(s));
+            C[k] = rc.scaled * (sh.mref + lg2_sum_exact(s) + cCY);
             gCx[k] = (sh.gx.x + sh.gx.y) / s;
             gCy[k] = (sh.gy.x + sh.gy.y) / s;
           }
@@ -573,7 +585,7 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
 #pragma unroll
         for (int k = 0; k < kRows; ++k) {
           if (ridx[k] < 0) continue;
-          (own ? potS : potC)[ridx[k]] = rc.scaled * lse[k];
+          (own ? potS : potC)[ridx[k]] = rc.scaled * (lse[k] + (own ? cSY : cCX));
         }
       }
     }
