@@ -86,6 +86,100 @@ __device__ __forceinline__ RoundOut<CH, GRAD> fast_round(const float* __restrict
   return o;
 }
 
+// ---- rolled forms (runtime chunk count) ---------------------------------------------------------------------------------
+// ncu on the fully unrolled, per-chunk-count templated rounds showed `no_instruction` as the top stall (3 cycles per issued
+// instruction, 13 % issue utilisation): one warp per sub-partition streams ~500 straight-line instructions per round out of
+// the L1.5 instruction cache and never reuses them.  The rolled forms run the same arithmetic (bit-identical sums: same
+// accumulators, same order) from loops of ~40 instructions that stay in the L0 instruction cache, at the price of
+// recomputing the arguments in the second pass (packed FMAs, cheap next to the ex2) instead of holding them in registers.
+__device__ __forceinline__ float rolled_max(const float* __restrict__ cx, const float* __restrict__ cy,
+                                            const float* __restrict__ hp, int c0, int c1, float2 npx, float2 npy, float2 coef2) {
+  float m = kNegBig;
+#pragma unroll 1
+  for (int c = c0; c < c1; ++c) {
+    const float4 X = reinterpret_cast<const float4*>(cx)[c];
+    const float4 Y = reinterpret_cast<const float4*>(cy)[c];
+    const float4 H = reinterpret_cast<const float4*>(hp)[c];
+    const float2 d0 = __fadd2_rn(make_float2(X.x, X.y), npx), d1 = __fadd2_rn(make_float2(X.z, X.w), npx);
+    const float2 e0 = __fadd2_rn(make_float2(Y.x, Y.y), npy), e1 = __fadd2_rn(make_float2(Y.z, Y.w), npy);
+    const float2 v0 = __ffma2_rn(__ffma2_rn(e0, e0, __fmul2_rn(d0, d0)), coef2, make_float2(H.x, H.y));
+    const float2 v1 = __ffma2_rn(__ffma2_rn(e1, e1, __fmul2_rn(d1, d1)), coef2, make_float2(H.z, H.w));
+    m = fmaxf(m, fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y)));
+  }
+  return m;
+}
+
+template <bool GRAD>
+__device__ __forceinline__ void rolled_sum(const float* __restrict__ cx, const float* __restrict__ cy,
+                                           const float* __restrict__ hp, int c0, int c1, float2 npx, float2 npy, float2 coef2,
+                                           float m, float& ssum, float& gxo, float& gyo) {
+  const float2 nm = make_float2(-m, -m);
+  float2 s = make_float2(0.f, 0.f), gx = s, gy = s;
+#pragma unroll 1
+  for (int c = c0; c < c1; ++c) {
+    const float4 X = reinterpret_cast<const float4*>(cx)[c];
+    const float4 Y = reinterpret_cast<const float4*>(cy)[c];
+    const float4 H = reinterpret_cast<const float4*>(hp)[c];
+    const float2 d0 = __fadd2_rn(make_float2(X.x, X.y), npx), d1 = __fadd2_rn(make_float2(X.z, X.w), npx);
+    const float2 e0 = __fadd2_rn(make_float2(Y.x, Y.y), npy), e1 = __fadd2_rn(make_float2(Y.z, Y.w), npy);
+    const float2 a0 = __fadd2_rn(__ffma2_rn(__ffma2_rn(e0, e0, __fmul2_rn(d0, d0)), coef2, make_float2(H.x, H.y)), nm);
+    const float2 a1 = __fadd2_rn(__ffma2_rn(__ffma2_rn(e1, e1, __fmul2_rn(d1, d1)), coef2, make_float2(H.z, H.w)), nm);
+    const float2 p0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
+    const float2 p1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+    s = __fadd2_rn(s, __fadd2_rn(p0, p1));
+    if (GRAD) {
+      gx = __fadd2_rn(gx, __ffma2_rn(p1, d1, __fmul2_rn(p0, d0)));
+      gy = __fadd2_rn(gy, __ffma2_rn(p1, e1, __fmul2_rn(p0, e0)));
+    }
+  }
+  ssum = s.x + s.y; gxo = gx.x + gx.y; gyo = gy.x + gy.y;
+}
+
+struct RoundOutRt {
+  double lseX, lseY;
+  float gXx, gXy, sX, gYx, gYy, sY;
+};
+
+template <bool GRAD>
+__device__ __forceinline__ RoundOutRt fast_round_rt(const float* __restrict__ cx, const float* __restrict__ cy,
+                                                    const float* __restrict__ hp, int nchx, int nch, float px, float py,
+                                                    float coef) {
+  const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py), coef2 = make_float2(coef, coef);
+  const float mX = rolled_max(cx, cy, hp, 0, nchx, npx, npy, coef2);
+  const float mY = rolled_max(cx, cy, hp, nchx, nch, npx, npy, coef2);
+  RoundOutRt o;
+  rolled_sum<GRAD>(cx, cy, hp, 0, nchx, npx, npy, coef2, mX, o.sX, o.gXx, o.gXy);
+  rolled_sum<GRAD>(cx, cy, hp, nchx, nch, npx, npy, coef2, mY, o.sY, o.gYx, o.gYy);
+  o.lseX = (double)mX + lg2_sum(o.sX);
+  o.lseY = (double)mY + lg2_sum(o.sY);
+  return o;
+}
+
+// rolled high-precision sweep over chunks [c0, c1) relative to ref (see hi_round)
+template <bool GRAD>
+__device__ __forceinline__ void hi_sum_rt(const double* __restrict__ d2s, const double* __restrict__ hd,
+                                          const float* __restrict__ cx, const float* __restrict__ cy, int c0, int c1,
+                                          float pxf, float pyf, double coef, double ref, float& ssum, float& gxo, float& gyo) {
+  float s = 0.f, gx = 0.f, gy = 0.f;
+#pragma unroll 1
+  for (int c = c0; c < c1; ++c) {
+    const int j = 4 * c;
+    const double2 H0 = *reinterpret_cast<const double2*>(hd + j), H1 = *reinterpret_cast<const double2*>(hd + j + 2);
+    const double u0 = fma(coef, d2s[(j + 0) * 32], H0.x - ref), u1 = fma(coef, d2s[(j + 1) * 32], H0.y - ref);
+    const double u2 = fma(coef, d2s[(j + 2) * 32], H1.x - ref), u3 = fma(coef, d2s[(j + 3) * 32], H1.y - ref);
+    const float e0 = ex2_approx(f64_to_f32_trunc_nz(u0)), e1 = ex2_approx(f64_to_f32_trunc_nz(u1));
+    const float e2 = ex2_approx(f64_to_f32_trunc_nz(u2)), e3 = ex2_approx(f64_to_f32_trunc_nz(u3));
+    s += (e0 + e1) + (e2 + e3);
+    if (GRAD) {
+      const float4 XF = *reinterpret_cast<const float4*>(cx + j);
+      const float4 YF = *reinterpret_cast<const float4*>(cy + j);
+      gx += fmaf(e0, XF.x - pxf, fmaf(e1, XF.y - pxf, fmaf(e2, XF.z - pxf, e3 * (XF.w - pxf))));
+      gy += fmaf(e0, YF.x - pyf, fmaf(e1, YF.y - pyf, fmaf(e2, YF.z - pyf, e3 * (YF.w - pyf))));
+    }
+  }
+  ssum = s; gxo = gx; gyo = gy;
+}
+
 // High-precision round (the cold ones among the last KDOT_HI_ROUNDS rounds, see kdot_common.cuh): the soft-min argument
 //   t_ij = h_j + coef * |p_i - p_j|^2   (|h|, |coef d^2| ~ 1e3..1e4, t - max_j t = O(1) for the pairs that matter)
 // is formed in float64 from float64 copies of the columns and offsets; only t - ref is re-packed to fp32 for the
@@ -279,15 +373,125 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
   gCx = gYx / sY; gCy = gYy / sY;
 }
 
+// rolled variant of fast_solve (runtime chunk count, one instantiation): see the note at rolled_max
+__device__ __forceinline__ void fast_solve_rt(const FastCtx& c, int nch, int nrounds, const ImgSched& is, const SinkhornParams& prm,
+                                           RoundConst mine, double& S_out, double& C_out,
+                                           float& gSx, float& gSy, float& gCx, float& gCy, RoundConst& rc_last) {
+  const int lane = threadIdx.x & 31;
+  const float eps0 = (float)is.eps0;
+  double potS = 0.0, potC = 0.0;
+  float hmag = 0.f;  // max |h| over this slot's columns, as published for the current round (hi_mag_factor test)
+  double addX = 0.0, addY = 0.0;  // centres of the consumed student / teacher column offsets (0 in the init round)
+  int cur = 0;
+  for (int r = 0; r < nrounds - 1; ++r) {
+    if (r >= 32 && (r & 31) == 0)  // schedules longer than 32 rounds: next block of constants
+      mine = make_round_const(r + lane, is, prm.sp);
+    const double scaled = __shfl_sync(0xffffffffu, mine.scaled, r & 31);
+    const double hmuld = __shfl_sync(0xffffffffu, mine.hmuld, r & 31);
+    double lseX, lseY;
+    const float coef = __shfl_sync(0xffffffffu, mine.coef, r & 31);
+    const float eps = __shfl_sync(0xffffffffu, mine.eps, r & 31);
+    // centres for the h this round publishes (potentials as they stand after round r - 1; 0 before the first update)
+#ifndef KDOT_SMALL_NO_CENTRE
+    const double pSX = __shfl_sync(0xffffffffu, potS, 0), pSY = __shfl_sync(0xffffffffu, potS, c.nstu);
+    const double pCX = __shfl_sync(0xffffffffu, potC, 0), pCY = __shfl_sync(0xffffffffu, potC, c.nstu);
+#else
+    const double pSX = 0.0, pSY = 0.0, pCX = 0.0, pCY = 0.0;
+#endif
+    const double ownS = c.isx ? pSX : pSY, ownC = c.isx ? pCX : pCY;   // this lane's column: which set it belongs to
+    const double refX = c.isx ? pSX : pCX;   // student columns: student rows read h^S[X], teacher rows h^C[X]
+    const double refY = c.isx ? pCY : pSY;   // teacher columns: student rows read h^C[Y], teacher rows h^S[Y]
+    const float* hp = c.hb + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
+    if (!(is_hi_round(r, nrounds, eps, eps0) && hmag * hi_mag_factor(r, nrounds) > 1.0f)) {
+      const RoundOutRt o = fast_round_rt<false>(c.cx, c.cy, hp, c.nchx, nch, c.px, c.py, coef);
+      lseX = o.lseX; lseY = o.lseY;
+    } else {
+      const double coefd = __shfl_sync(0xffffffffu, mine.coefd, r & 31);
+      const double* hpd = c.hbd + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
+      const float2 npx = make_float2(-c.px, -c.px), npy = make_float2(-c.py, -c.py), coef2 = make_float2(coef, coef);
+      double refX = (double)rolled_max(c.cx, c.cy, hp, 0, c.nchx, npx, npy, coef2) + 2.0;
+      double refY = (double)rolled_max(c.cx, c.cy, hp, c.nchx, nch, npx, npy, coef2) + 2.0;
+      if ((hmag + (float)fabs(refX) + (float)fabs(refY)) * 9.5e-7f > 1.0f) hi_reference_f64(c.d2s, hpd, 4 * nch, 4 * c.nchx, coefd, refX, refY);
+      float sx, sy, g0, g1;
+      hi_sum_rt<false>(c.d2s, hpd, c.cx, c.cy, 0, c.nchx, c.px, c.py, coefd, refX, sx, g0, g1);
+      hi_sum_rt<false>(c.d2s, hpd, c.cx, c.cy, c.nchx, nch, c.px, c.py, coefd, refY, sy, g0, g1);
+      lseX = refX + lg2_sum(sx); lseY = refY + lg2_sum(sy);
+    }
+    lseX += addX; lseY += addY;   // the centres the consumed h was published relative to (see below)
+    const double nS = scaled * (c.isx ? lseX : lseY);
+    const double nC = scaled * (c.isx ? lseY : lseX);
+    potS = r == 0 ? nS : 0.5 * (potS + nS);
+    potC = r == 0 ? nC : 0.5 * (potC + nC);
+    // Centred offsets: with unequal total masses every potential of a cloud carries a common term of order
+    // rho * log(mass ratio) / eps (1e4 log2-units at eps = 1e-6) that cancels in h_j - max_j h_j; each of the four
+    // (type S/C, cloud) sets is published relative to the potential its first point had ONE ROUND EARLIER (read at the top
+    // of the round, off the critical path) and the same constant is added
+    // back to the log-sum-exp in float64.  What is left in |h| is the variation across the cloud -- which is what decides
+    // whether fp32 pair arguments are accurate enough (hi_mag_factor).
+    addX = refX * hmuld;
+    addY = refY * hmuld;
+    hmag = 0.f;
+    if (c.act) {
+      const double hS = fma(potS - ownS, hmuld, c.lw2d), hC = fma(potC - ownC, hmuld, c.lw2d);
+      hmag = fmaxf(fabsf((float)hS), fabsf((float)hC));
+      float* hn = c.hb + (cur ^ 1) * (2 * kFastMaxCols);
+      double* hnd = c.hbd + (cur ^ 1) * (2 * kFastMaxCols);
+      hn[c.col] = (float)(c.isx ? hS : hC);                  // view 0: what student rows read for this column
+      hn[kFastMaxCols + c.col] = (float)(c.isx ? hC : hS);   // view 1: what teacher rows read
+      hnd[c.col] = c.isx ? hS : hC;
+      hnd[kFastMaxCols + c.col] = c.isx ? hC : hS;
+    }
+    __syncwarp();
+    hmag = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(hmag)));  // non-negative floats order like their bits
+    cur ^= 1;
+  }
+  const int r = nrounds - 1;
+  if (r >= 32 && (r & 31) == 0)
+    mine = make_round_const(r + lane, is, prm.sp);
+  rc_last.coef = __shfl_sync(0xffffffffu, mine.coef, r & 31);
+  rc_last.scale = __shfl_sync(0xffffffffu, mine.scale, r & 31);
+  rc_last.hmul = 0.f;
+  rc_last.eps = __shfl_sync(0xffffffffu, mine.eps, r & 31);
+  rc_last.coefd = __shfl_sync(0xffffffffu, mine.coefd, r & 31);
+  rc_last.scaled = __shfl_sync(0xffffffffu, mine.scaled, r & 31);
+  rc_last.hmuld = 0.0;
+  double lseX, lseY;
+  float sX, sY, gXx, gXy, gYx, gYy;
+  const float* hp = c.hb + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
+  if (!(is_hi_round(r, nrounds, rc_last.eps, eps0) && hmag * hi_mag_factor(r, nrounds) > 1.0f)) {
+    const RoundOutRt o = fast_round_rt<true>(c.cx, c.cy, hp, c.nchx, nch, c.px, c.py, rc_last.coef);
+    lseX = o.lseX; lseY = o.lseY; sX = o.sX; sY = o.sY;
+    gXx = o.gXx; gXy = o.gXy; gYx = o.gYx; gYy = o.gYy;
+  } else {
+    const double* hpd = c.hbd + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
+    const float2 npx = make_float2(-c.px, -c.px), npy = make_float2(-c.py, -c.py), coef2 = make_float2(rc_last.coef, rc_last.coef);
+    double refX = (double)rolled_max(c.cx, c.cy, hp, 0, c.nchx, npx, npy, coef2) + 2.0;
+    double refY = (double)rolled_max(c.cx, c.cy, hp, c.nchx, nch, npx, npy, coef2) + 2.0;
+    if ((hmag + (float)fabs(refX) + (float)fabs(refY)) * 9.5e-7f > 1.0f) hi_reference_f64(c.d2s, hpd, 4 * nch, 4 * c.nchx, rc_last.coefd, refX, refY);
+    hi_sum_rt<true>(c.d2s, hpd, c.cx, c.cy, 0, c.nchx, c.px, c.py, rc_last.coefd, refX, sX, gXx, gXy);
+    hi_sum_rt<true>(c.d2s, hpd, c.cx, c.cy, c.nchx, nch, c.px, c.py, rc_last.coefd, refY, sY, gYx, gYy);
+    lseX = refX + lg2_sum(sX); lseY = refY + lg2_sum(sY);
+  }
+  lseX += addX; lseY += addY;
+  S_out = rc_last.scaled * (c.isx ? lseX : lseY);
+  C_out = rc_last.scaled * (c.isx ? lseY : lseX);
+  // barycentric displacements  sum_j W_ij (p_j - p_i)  against own / other cloud (student rows use them)
+  gSx = gXx / sX; gSy = gXy / sX;
+  gCx = gYx / sY; gCy = gYy / sY;
+}
+
+
 // The B slots of an image are spread over a thread-block cluster of `split` CTAs (B/split warps each) so that a
 // small batch still covers the whole chip with about one warp per SM sub-partition: the rounds are bound by the
 // per-sub-partition SFU / FP32 pipes, not by occupancy.  The cluster is only needed twice: a barrier before the
 // in-place normalisation (every CTA reads all slots for the bounding box) and the fixed-order sum over slots,
 // which rank 0 performs on values its peers wrote into its shared memory (DSMEM).
-#ifndef KDOT_SMALL_MINBLOCKS
-#define KDOT_SMALL_MINBLOCKS 1
-#endif
-__global__ void __launch_bounds__(256, KDOT_SMALL_MINBLOCKS) kdot_small_fast_kernel(SinkhornParams prm, int split) {
+// ROLLED = false: per-chunk-count unrolled rounds, arguments held in registers (176 registers, one CTA per SM): lowest latency
+// when the batch gives every SM sub-partition at most one warp (ape_b64: 26.6 vs 28.9 us).  ROLLED = true: the rolled rounds
+// (120 registers, two CTAs per SM, L0-resident loops): 20 % more throughput once the grid exceeds one CTA per SM (1024 images:
+// 111 vs 133 us).  launch_small picks by grid size.
+template <bool ROLLED>
+__global__ void __launch_bounds__(256, ROLLED ? 2 : 1) kdot_small_fast_kernel(SinkhornParams prm, int split) {
   cg::cluster_group cluster = cg::this_cluster();
   const int img = blockIdx.x / split, part = blockIdx.x - img * split;
   const int wpc = prm.B / split;  // warps (slots) per CTA
@@ -431,11 +635,15 @@ __global__ void __launch_bounds__(256, KDOT_SMALL_MINBLOCKS) kdot_small_fast_ker
   const RoundConst mine = make_round_const(lane, is, prm.sp);  // lane r holds the constants of round r
   dbg_stamp(prm, img, 4);
   const int ch = (Nq + Mq) >> 2;
-  switch (ch) {
+  if (!ROLLED) {
+    switch (ch) {
 #define KDOT_CASE(K) case K: fast_solve<K>(c, nrounds, is, prm, mine, S, C, gSx, gSy, gCx, gCy, rc); break;
-    KDOT_CASE(2) KDOT_CASE(3) KDOT_CASE(4) KDOT_CASE(5) KDOT_CASE(6) KDOT_CASE(7) KDOT_CASE(8) KDOT_CASE(9)
-    default: fast_solve<kFastMaxCH>(c, nrounds, is, prm, mine, S, C, gSx, gSy, gCx, gCy, rc); break;
+      KDOT_CASE(2) KDOT_CASE(3) KDOT_CASE(4) KDOT_CASE(5) KDOT_CASE(6) KDOT_CASE(7) KDOT_CASE(8) KDOT_CASE(9)
+      default: fast_solve<kFastMaxCH>(c, nrounds, is, prm, mine, S, C, gSx, gSy, gCx, gCy, rc); break;
 #undef KDOT_CASE
+    }
+  } else {
+    fast_solve_rt(c, ch, nrounds, is, prm, mine, S, C, gSx, gSy, gCx, gCy, rc);
   }
 
   dbg_stamp(prm, img, 5);
@@ -489,11 +697,13 @@ cudaError_t launch_small(const SinkhornParams& prm, int max_n, int max_m, cudaSt
     while (split < 8 && prm.B % (split * 2) == 0 && (long long)prm.nimg * split * 2 <= (long long)sm_count) split *= 2;
     const int wpc = prm.B / split;
     const size_t smem = (size_t)wpc * kFastWarpDoubles * sizeof(double);
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(kdot_small_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool rolled = (long long)prm.nimg * split > (long long)sm_count;  // more than one CTA per SM: throughput variant
+    static size_t configured[2] = {48 * 1024, 48 * 1024};
+    if (smem > configured[rolled]) {
+      cudaError_t e = rolled ? cudaFuncSetAttribute(kdot_small_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                             : cudaFuncSetAttribute(kdot_small_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      configured = smem;
+      configured[rolled] = smem;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(prm.nimg * split);
@@ -507,7 +717,8 @@ cudaError_t launch_small(const SinkhornParams& prm, int max_n, int max_m, cudaSt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kdot_small_fast_kernel, prm, split);
+    return rolled ? cudaLaunchKernelEx(&cfg, kdot_small_fast_kernel<true>, prm, split)
+                  : cudaLaunchKernelEx(&cfg, kdot_small_fast_kernel<false>, prm, split);
   }
 }
 
