@@ -364,10 +364,10 @@ def kernel_name(max_n, max_m, launches_per_step):
 
 def ncu_traffic_bytes(kernel, workload):
     """DRAM bytes (read + write) of one launch of `kernel` from the committed `ncu --set full` summary of the same
-    workload (profiles/r01_prof_*_ncu_summary.txt), or None when no capture of that kernel ON THAT WORKLOAD is on file."""
+    workload (profiles/r02_prof_*_ncu_summary.txt), or None when no capture of that kernel ON THAT WORKLOAD is on file."""
     tag = {("kdot_small_fast_kernel", "ape_b64"): "small_fast", ("kdot_stream_kernel", "dense_b32"): "stream",
-           ("kdot_tiled_kernel", "multi_b64"): "tiled"}.get((kernel, workload))
-    path = os.path.join(ROOT, "profiles", f"r01_prof_{tag}_ncu_summary.txt")
+           ("kdot_stream_kernel", "zebra_b8"): "stream_zebra", ("kdot_tiled_kernel", "multi_b64"): "tiled"}.get((kernel, workload))
+    path = os.path.join(ROOT, "profiles", f"r02_prof_{tag}_ncu_summary.txt")
     if tag is None or not os.path.exists(path):
         return None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -619,7 +619,7 @@ def main():
     roofline["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/)"
     if roofline["kernel"] == "kdot_stream_kernel":
         roofline["traffic_note"] = ("includes the write-back / re-fetch of the kernel's L2-resident scratch (staged clouds, potentials, "
-                                    "tile maxima: ~50 B per point) under ncu's cache control; < 0.2 % of HBM bandwidth, the kernel is SFU/FP32 bound")
+                                    "float64 potentials, fp32 head + tail of h, tile maxima: ~70 B per point, rewritten every round) under ncu's cache control; < 0.5 % of HBM bandwidth, the kernel is SFU/FP32 bound")
 
     # end to end through the host-buffer C-ABI call
     e2e_dt, h2d, d2h, mean_loss = host_e2e(batch, local_rank, args.steps, args.warmup, barrier, cfg)
