@@ -250,10 +250,13 @@ struct TileSkip {
 constexpr float kSigThr = 1.0f / 16384.0f;
 // Stream-kernel value of kHiMagnitude (kdot_common.cuh).  Clouds of several hundred points and more: the max-norm of the
 // d/dx error is set by a few ill-conditioned cells (near-ties between neighbours) that react to the 2^-22 error of
-// ex2.approx itself -- 2e-5..1.7e-4 with or without float64 arguments (tools/accuracy_report.py on 16 streaming cases:
+// ex2.approx itself -- 2e-5..1.7e-4 with or without float64 arguments (tools/accuracy_stream_scan.py, 16 streaming cases:
 // mean 4e-5 vs 6e-5) -- while the screened float64 sub-tiles cost dense_b32 12 %.  They are therefore reserved for
 // problems whose CENTRED offsets exceed 8192 log2-units in the last round (fp32 argument error > 5e-4: wide, sparse clouds).
-constexpr float kStreamHiMagnitude = 4096.0f;
+#ifndef KDOT_STREAM_HI_MAG
+#define KDOT_STREAM_HI_MAG 4096.0f
+#endif
+constexpr float kStreamHiMagnitude = KDOT_STREAM_HI_MAG;
 
 struct HiArgs {
   const float* chlo;  // fp32 tail of h for the column set (same indexing as ch)
