@@ -41,8 +41,8 @@ struct RoundConst {
 // float64 -- but only while they are COLD (eps < eps_0 / 256): in a warm round |coef * d^2| <= 0.72 * eps_0 / eps < 185
 // log2-units, where an fp32 argument is accurate to ~1e-5 anyway.  Errors made in earlier rounds are halved by every
 // averaged update that follows, so six trailing rounds leave less than 2^-6 of an fp32 potential's rounding error.
-__device__ __forceinline__ bool is_hi_round(int r, int nrounds, float eps, float eps0) {
-  return r >= nrounds - KDOT_HI_ROUNDS && eps * 256.0f < eps0;
+__device__ __forceinline__ bool is_hi_round(int r, int nrounds, float eps, float eps0, int last = KDOT_HI_ROUNDS) {
+  return r >= nrounds - last && eps * 256.0f < eps0;
 }
 
 // Magnitude test that goes with is_hi_round: an fp32 soft-min argument carries an error of ~2^-24 max(|h_j|, |coef d^2|),
@@ -250,6 +250,30 @@ __device__ __forceinline__ ImgSched image_schedule(float diam_f, const SchedPara
   return is;
 }
 
+// image_schedule evaluated by a whole warp (every lane gets the result): the table is scanned by two ballots instead of a
+// serial loop of dependent constant-bank loads (the predicate is monotonic in k, so the length is its population count).
+__device__ __forceinline__ ImgSched image_schedule_warp(float diam_f, const SchedParams& sp, int lane) {
+  static_assert(KDOT_SCHED_TABLE <= 64, "two ballots cover the table");
+  const double diam = (double)diam_f;
+  const double eps0 = sp.p == 2.0 ? diam * diam : diam;  // p in {1, 2}
+  const bool in0 = lane < KDOT_SCHED_TABLE && eps0 * sp.pow_table[lane < KDOT_SCHED_TABLE ? lane : 0] > sp.eps_final;
+  const bool in1 = lane + 32 < KDOT_SCHED_TABLE && eps0 * sp.pow_table[lane + 32 < KDOT_SCHED_TABLE ? lane + 32 : 0] > sp.eps_final;
+  const int len = __popc(__ballot_sync(0xffffffffu, in0)) + __popc(__ballot_sync(0xffffffffu, in1));
+  if (len >= KDOT_SCHED_TABLE) return image_schedule_slow(diam, sp.p, sp.log_blur_p, sp.log_scaling_p, eps0);
+  // exact ties (see image_schedule): the same 1e-9 band around eps_final, written without divisions
+  const double last_in = len > 0 ? eps0 * sp.pow_table[len - 1] : 2.0 * sp.eps_final;
+  const double first_out = eps0 * sp.pow_table[len];
+  if (last_in < sp.eps_final * (1.0 + 1e-9) || first_out > sp.eps_final * (1.0 - 1e-9))
+    return image_schedule_slow(diam, sp.p, sp.log_blur_p, sp.log_scaling_p, eps0);
+  ImgSched is;
+  is.nits = len + 2;
+  is.slow = 0;
+  is.start = 0.0;
+  is.delta = 0.0;
+  is.eps0 = eps0;
+  return is;
+}
+
 // Round r of the kernel's flattened loop: r = 0 init (eps_s[0]), 1..nits the loop, nits+1 the last extrapolation.
 __device__ __forceinline__ int round_to_sched(int r, int nits) {
   if (r == 0) return 0;
@@ -271,10 +295,10 @@ __device__ __forceinline__ double schedule_eps(int t, const ImgSched& is, const 
 __device__ __forceinline__ RoundConst make_round_const(int r, const ImgSched& is, const SchedParams& sp) {
   const double eps = schedule_eps(round_to_sched(r, is.nits), is, sp);
   const double eps_next = schedule_eps(round_to_sched(r + 1, is.nits), is, sp);
-  const double lam = sp.rho < 0.0 ? 1.0 : 1.0 / (1.0 + eps / sp.rho);
   RoundConst rc;
   rc.coefd = (sp.p == 2.0 ? -0.5 : -1.0) * 1.4426950408889634 / eps;  // cost |d|^2/2 (p = 2) or |d| (p = 1)
-  rc.scaled = -lam * eps * 0.6931471805599453;
+  // -lambda eps ln 2 with lambda = 1 / (1 + eps/rho) = rho / (rho + eps): one division
+  rc.scaled = sp.rho < 0.0 ? -eps * 0.6931471805599453 : -(sp.rho * eps * 0.6931471805599453) / (sp.rho + eps);
   rc.hmuld = 1.4426950408889634 / eps_next;
   rc.coef = (float)rc.coefd;
   rc.scale = (float)rc.scaled;

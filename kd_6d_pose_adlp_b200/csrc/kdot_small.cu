@@ -23,9 +23,13 @@ namespace cg = cooperative_groups;
 
 namespace kdot {
 
+#ifndef KDOT_SMALL_HI_ROUNDS
+#define KDOT_SMALL_HI_ROUNDS KDOT_HI_ROUNDS
+#endif
+constexpr int kSmallHiRounds = KDOT_SMALL_HI_ROUNDS;  // trailing rounds that may take float64 pair arguments (kdot_common.cuh)
 constexpr int kFastMaxCols = 40;  // padded columns of the fast path (<= 32 points + padding)
 constexpr int kFastMaxCH = kFastMaxCols / 4;
-constexpr int kFastWarpDoubles = (4 + 32 + 3) * kFastMaxCols;  // per-warp shared memory in units of 8 bytes (see the kernel)
+constexpr int kFastWarpDoubles = (4 + 32 + 3) * kFastMaxCols + 4;  // per-warp shared memory in units of 8 bytes (see the kernel)
 
 // =========================================================================================================
 // fast path
@@ -261,6 +265,7 @@ struct FastCtx {
   float* cx; float* cy; float* hb;  // per-warp smem: cx[40], cy[40], hb[2 buffers][2 views][40]
   double* hbd;   // float64 copy of hb (high-precision rounds)
   double* d2s;   // [40 columns][32 lanes] float64 squared distances of this lane's point to every column
+  double* ctr;   // centres of the published offsets: (potS, potC) of the first student point | of the first teacher point
   int nchx;                         // student chunks (padded student columns / 4)
   int nstu;                         // student points N: lanes [0, N) are student rows, [N, N + M) teacher rows
   bool act, isx;
@@ -285,6 +290,16 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
   for (int r = 0; r < nrounds - 1; ++r) {
     if (r >= 32 && (r & 31) == 0)  // schedules longer than 32 rounds: next block of constants
       mine = make_round_const(r + lane, is, prm.sp);
+#ifdef KDOT_SMALL_ROUND_STAMPS
+    {  // profiling aid (tools/microbench_small.py): SM clock at the start of 7 rounds, slots 8..14 of the debug buffer
+#ifdef KDOT_SMALL_ROUND_STAMPS_TAIL
+      const int k = r - (nrounds - 8);   // the last 7 rounds before the gradient round; slot 15 = start of the gradient round
+#else
+      const int k = r;
+#endif
+      if (prm.dbg_clk && threadIdx.x == 0 && k >= 0 && k < 7) prm.dbg_clk[(size_t)(blockIdx.x / (gridDim.x / prm.nimg)) * 16 + 8 + k] = clock64();
+    }
+#endif
     const double scaled = __shfl_sync(0xffffffffu, mine.scaled, r & 31);
     const double hmuld = __shfl_sync(0xffffffffu, mine.hmuld, r & 31);
     double lseX, lseY;
@@ -292,16 +307,18 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
     const float eps = __shfl_sync(0xffffffffu, mine.eps, r & 31);
     // centres for the h this round publishes (potentials as they stand after round r - 1; 0 before the first update)
 #ifndef KDOT_SMALL_NO_CENTRE
-    const double pSX = __shfl_sync(0xffffffffu, potS, 0), pSY = __shfl_sync(0xffffffffu, potS, c.nstu);
-    const double pCX = __shfl_sync(0xffffffffu, potC, 0), pCY = __shfl_sync(0xffffffffu, potC, c.nstu);
+    // (potS, potC) of the first student point and of the first teacher point, left in shared memory by their lanes at
+    // the end of the previous round: two broadcast LDS.128 instead of eight shuffles (330 cycles per round, measured)
+    const double2 own = *reinterpret_cast<const double2*>(c.ctr + (c.isx ? 0 : 2));   // this lane's own set
+    const double2 oth = *reinterpret_cast<const double2*>(c.ctr + (c.isx ? 2 : 0));
+    const double ownS = own.x, ownC = own.y;
+    const double refX = c.isx ? own.x : oth.y;   // student columns: student rows read h^S[X], teacher rows h^C[X]
+    const double refY = c.isx ? oth.y : own.x;   // teacher columns: student rows read h^C[Y], teacher rows h^S[Y]
 #else
-    const double pSX = 0.0, pSY = 0.0, pCX = 0.0, pCY = 0.0;
+    const double ownS = 0.0, ownC = 0.0, refX = 0.0, refY = 0.0;
 #endif
-    const double ownS = c.isx ? pSX : pSY, ownC = c.isx ? pCX : pCY;   // this lane's column: which set it belongs to
-    const double refX = c.isx ? pSX : pCX;   // student columns: student rows read h^S[X], teacher rows h^C[X]
-    const double refY = c.isx ? pCY : pSY;   // teacher columns: student rows read h^C[Y], teacher rows h^S[Y]
     const float* hp = c.hb + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
-    if (!(is_hi_round(r, nrounds, eps, eps0) && hmag * hi_mag_factor(r, nrounds) > 1.0f)) {
+    if (!(is_hi_round(r, nrounds, eps, eps0, kSmallHiRounds) && hmag * hi_mag_factor(r, nrounds) > 1.0f)) {
       const RoundOut<CH, false> o = fast_round<CH, false>(c.cx, c.cy, hp, c.nchx, c.px, c.py, coef);
       lseX = o.lseX; lseY = o.lseY;
     } else {
@@ -336,11 +353,16 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
       hnd[c.col] = c.isx ? hS : hC;
       hnd[kFastMaxCols + c.col] = c.isx ? hC : hS;
     }
+    if (lane == 0 || lane == c.nstu)   // next round's centres (all lanes read the current ones at the top of this round)
+      *reinterpret_cast<double2*>(c.ctr + (lane == 0 ? 0 : 2)) = make_double2(potS, potC);
     __syncwarp();
     hmag = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(hmag)));  // non-negative floats order like their bits
     cur ^= 1;
   }
   const int r = nrounds - 1;
+#ifdef KDOT_SMALL_ROUND_STAMPS
+  if (prm.dbg_clk && threadIdx.x == 0) prm.dbg_clk[(size_t)(blockIdx.x / (gridDim.x / prm.nimg)) * 16 + 15] = clock64();
+#endif
   if (r >= 32 && (r & 31) == 0)
     mine = make_round_const(r + lane, is, prm.sp);
   rc_last.coef = __shfl_sync(0xffffffffu, mine.coef, r & 31);
@@ -353,7 +375,7 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
   double lseX, lseY;
   float sX, sY, gXx, gXy, gYx, gYy;
   const float* hp = c.hb + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
-  if (!(is_hi_round(r, nrounds, rc_last.eps, eps0) && hmag * hi_mag_factor(r, nrounds) > 1.0f)) {
+  if (!(is_hi_round(r, nrounds, rc_last.eps, eps0, kSmallHiRounds) && hmag * hi_mag_factor(r, nrounds) > 1.0f)) {
     const RoundOut<CH, true> o = fast_round<CH, true>(c.cx, c.cy, hp, c.nchx, c.px, c.py, rc_last.coef);
     lseX = o.lseX; lseY = o.lseY; sX = o.sX; sY = o.sY;
     gXx = o.gXx; gXy = o.gXy; gYx = o.gYx; gYy = o.gYy;
@@ -393,16 +415,18 @@ __device__ __forceinline__ void fast_solve_rt(const FastCtx& c, int nch, int nro
     const float eps = __shfl_sync(0xffffffffu, mine.eps, r & 31);
     // centres for the h this round publishes (potentials as they stand after round r - 1; 0 before the first update)
 #ifndef KDOT_SMALL_NO_CENTRE
-    const double pSX = __shfl_sync(0xffffffffu, potS, 0), pSY = __shfl_sync(0xffffffffu, potS, c.nstu);
-    const double pCX = __shfl_sync(0xffffffffu, potC, 0), pCY = __shfl_sync(0xffffffffu, potC, c.nstu);
+    // (potS, potC) of the first student point and of the first teacher point, left in shared memory by their lanes at
+    // the end of the previous round: two broadcast LDS.128 instead of eight shuffles
+    const double2 own = *reinterpret_cast<const double2*>(c.ctr + (c.isx ? 0 : 2));   // this lane's own set
+    const double2 oth = *reinterpret_cast<const double2*>(c.ctr + (c.isx ? 2 : 0));
+    const double ownS = own.x, ownC = own.y;
+    const double refX = c.isx ? own.x : oth.y;   // student columns: student rows read h^S[X], teacher rows h^C[X]
+    const double refY = c.isx ? oth.y : own.x;   // teacher columns: student rows read h^C[Y], teacher rows h^S[Y]
 #else
-    const double pSX = 0.0, pSY = 0.0, pCX = 0.0, pCY = 0.0;
+    const double ownS = 0.0, ownC = 0.0, refX = 0.0, refY = 0.0;
 #endif
-    const double ownS = c.isx ? pSX : pSY, ownC = c.isx ? pCX : pCY;   // this lane's column: which set it belongs to
-    const double refX = c.isx ? pSX : pCX;   // student columns: student rows read h^S[X], teacher rows h^C[X]
-    const double refY = c.isx ? pCY : pSY;   // teacher columns: student rows read h^C[Y], teacher rows h^S[Y]
     const float* hp = c.hb + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
-    if (!(is_hi_round(r, nrounds, eps, eps0) && hmag * hi_mag_factor(r, nrounds) > 1.0f)) {
+    if (!(is_hi_round(r, nrounds, eps, eps0, kSmallHiRounds) && hmag * hi_mag_factor(r, nrounds) > 1.0f)) {
       const RoundOutRt o = fast_round_rt<false>(c.cx, c.cy, hp, c.nchx, nch, c.px, c.py, coef);
       lseX = o.lseX; lseY = o.lseY;
     } else {
@@ -441,6 +465,8 @@ __device__ __forceinline__ void fast_solve_rt(const FastCtx& c, int nch, int nro
       hnd[c.col] = c.isx ? hS : hC;
       hnd[kFastMaxCols + c.col] = c.isx ? hC : hS;
     }
+    if (lane == 0 || lane == c.nstu)   // next round's centres (all lanes read the current ones at the top of this round)
+      *reinterpret_cast<double2*>(c.ctr + (lane == 0 ? 0 : 2)) = make_double2(potS, potC);
     __syncwarp();
     hmag = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(hmag)));  // non-negative floats order like their bits
     cur ^= 1;
@@ -458,7 +484,7 @@ __device__ __forceinline__ void fast_solve_rt(const FastCtx& c, int nch, int nro
   double lseX, lseY;
   float sX, sY, gXx, gXy, gYx, gYy;
   const float* hp = c.hb + cur * (2 * kFastMaxCols) + (c.isx ? 0 : kFastMaxCols);
-  if (!(is_hi_round(r, nrounds, rc_last.eps, eps0) && hmag * hi_mag_factor(r, nrounds) > 1.0f)) {
+  if (!(is_hi_round(r, nrounds, rc_last.eps, eps0, kSmallHiRounds) && hmag * hi_mag_factor(r, nrounds) > 1.0f)) {
     const RoundOutRt o = fast_round_rt<true>(c.cx, c.cy, hp, c.nchx, nch, c.px, c.py, rc_last.coef);
     lseX = o.lseX; lseY = o.lseY; sX = o.sX; sY = o.sY;
     gXx = o.gXx; gXy = o.gXy; gYx = o.gYx; gYy = o.gYy;
@@ -498,7 +524,7 @@ __global__ void __launch_bounds__(256, ROLLED ? 2 : 1) kdot_small_fast_kernel(Si
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = part * wpc + warp;
   const int B = prm.B;
-  // per warp: float64 h[2][2][40] | d2[40][32], then fp32 cx[40] | cy[40] | h[2][2][40]
+  // per warp: float64 h[2][2][40] | d2[40][32], then fp32 cx[40] | cy[40] | h[2][2][40], then the 4 float64 centres
   extern __shared__ __align__(16) double s_dynd[];
   __shared__ double s_slot_loss[16];               // rank 0's copy collects all B slots
   double* wbase_d = s_dynd + (size_t)warp * kFastWarpDoubles;
@@ -518,6 +544,7 @@ __global__ void __launch_bounds__(256, ROLLED ? 2 : 1) kdot_small_fast_kernel(Si
   FastCtx c;
   c.cx = wbase_s; c.cy = wbase_s + kFastMaxCols; c.hb = wbase_s + 2 * kFastMaxCols;
   c.hbd = wbase_d; c.d2s = wbase_d + 4 * kFastMaxCols + lane;
+  c.ctr = wbase_d + (4 + 32 + 3) * kFastMaxCols;
   c.nchx = Nq >> 2;
   c.nstu = N;
   c.act = lane < P;
@@ -525,13 +552,16 @@ __global__ void __launch_bounds__(256, ROLLED ? 2 : 1) kdot_small_fast_kernel(Si
   c.col = c.isx ? lane : Nq + (lane - N);
   c.px = c.py = 0.f; c.wgt = 0.f; c.lw2 = 0.f; c.lw2d = 0.0;
 
-  // ---- every warp touches only ITS slot: load, normalise in place (the same thread reads and writes an element, so
-  //      there is no cross-warp hazard), log-weight.  The image-wide bounding box is assembled from the per-warp
-  //      boxes through shared memory, across the cluster through DSMEM. ----
-  __shared__ float s_box[16][4];
+  // ---- every warp loads ITS slot's points; the image-wide bounding box (geomloss' diameter spans all B slots) is
+  //      taken by every warp on its own from the raw points of all slots -- B loads per lane that hit the lines its
+  //      sibling warps fetch anyway -- instead of an exchange through (distributed) shared memory behind a cluster
+  //      barrier.  Division by a positive width is monotonic, so the box of the normalised points is the normalised box.
+  //      The in-place normalisation of the caller's buffer (loss_libs.py:8-12) is deferred until every warp of the
+  //      cluster has read the raw values: barrier arrive here, wait before the store at the end. ----
   float minx = 3.0e38f, miny = 3.0e38f, maxx = -3.0e38f, maxy = -3.0e38f;
   long long gidx = 0;
   float* base = nullptr;
+  float2 vnorm = make_float2(0.f, 0.f);
   if (c.act) {
     long long cell;
     long long s_cell, s_slot;
@@ -541,24 +571,32 @@ __global__ void __launch_bounds__(256, ROLLED ? 2 : 1) kdot_small_fast_kernel(Si
     gidx = cell * s_cell + (long long)slot * s_slot;
     float2 v = *reinterpret_cast<const float2*>(base + 2 * gidx);
     c.wgt = wsrc ? wsrc[gidx] : __fdiv_rn(1.0f, (float)(c.isx ? N : M));
+    const long long g0 = cell * s_cell;
+    for (int sl = 0; sl < B; ++sl) {
+      const float2 q = *reinterpret_cast<const float2*>(base + 2 * (g0 + (long long)sl * s_slot));
+      minx = fminf(minx, q.x); maxx = fmaxf(maxx, q.x);
+      miny = fminf(miny, q.y); maxy = fmaxf(maxy, q.y);
+    }
     if (prm.normalize) {
       v.x = __fdiv_rn(v.x, prm.w);
       v.y = __fdiv_rn(v.y, prm.h);
-      if (prm.normalize == 1) *reinterpret_cast<float2*>(base + 2 * gidx) = v;  // 2: keep the caller's buffer raw
     }
+    vnorm = v;
     c.px = v.x; c.py = v.y;
-    minx = maxx = v.x;
-    miny = maxy = v.y;
     c.lw2 = (c.wgt > 0.f ? logf(c.wgt) : kLogZeroWeight) * kLog2e;
     c.lw2d = (double)c.lw2;
   }
+  const bool store_norm = c.act && prm.normalize == 1;   // 2: keep the caller's buffer raw
   float* gx_out = prm.grad_xs + 2 * gidx;
   dbg_stamp(prm, img, 1);
   minx = warp_min(minx); miny = warp_min(miny); maxx = warp_max(maxx); maxy = warp_max(maxy);
-  if (lane == 0) { s_box[warp][0] = minx; s_box[warp][1] = miny; s_box[warp][2] = maxx; s_box[warp][3] = maxy; }
-  if (split > 1) cluster.sync(); else __syncthreads();
+  cluster.barrier_arrive();   // this warp's raw reads are done (the reductions above consumed them)
+  if (prm.normalize) {
+    minx = __fdiv_rn(minx, prm.w); maxx = __fdiv_rn(maxx, prm.w);
+    miny = __fdiv_rn(miny, prm.h); maxy = __fdiv_rn(maxy, prm.h);
+  }
 
-  if (N == 0 || M == 0) {  // skipped image (loss_libs.py:25-28); uniform over the CTA
+  if (N == 0 || M == 0) {  // skipped image (loss_libs.py:25-28); uniform over the cluster
     if (c.act && c.isx) {
       *reinterpret_cast<float2*>(gx_out) = make_float2(0.f, 0.f);
       if (prm.grad_ws) prm.grad_ws[gidx] = 0.f;
@@ -569,14 +607,9 @@ __global__ void __launch_bounds__(256, ROLLED ? 2 : 1) kdot_small_fast_kernel(Si
       prm.valid[img] = KDOT_IMG_SKIPPED;
       if (prm.nits_per_img) prm.nits_per_img[img] = 0;
     }
+    cluster.barrier_wait();
+    if (store_norm) *reinterpret_cast<float2*>(base + 2 * gidx) = vnorm;
     return;
-  }
-  for (int rk = 0; rk < split; ++rk) {
-    const float(*rb)[4] = split > 1 ? cluster.map_shared_rank(s_box, rk) : s_box;
-    for (int wi = 0; wi < wpc; ++wi) {
-      minx = fminf(minx, rb[wi][0]); miny = fminf(miny, rb[wi][1]);
-      maxx = fmaxf(maxx, rb[wi][2]); maxy = fmaxf(maxy, rb[wi][3]);
-    }
   }
   const float diam_f = bbox_diameter(minx, miny, maxx, maxy);
   dbg_stamp(prm, img, 2);
@@ -586,12 +619,12 @@ __global__ void __launch_bounds__(256, ROLLED ? 2 : 1) kdot_small_fast_kernel(Si
   if (!(diam_f > 0.f) || !isfinite(diam_f)) {
     status = KDOT_IMG_DEGENERATE;
   } else {
-    is = image_schedule(diam_f, prm.sp);
+    is = image_schedule_warp(diam_f, prm.sp, lane);
     nits = is.nits;
     nrounds = nits + 2;
     if (nrounds > KDOT_MAX_ROUNDS) status = KDOT_IMG_TOO_MANY_ROUNDS;
   }
-  if (status != KDOT_IMG_OK) {  // uniform over the CTA
+  if (status != KDOT_IMG_OK) {  // uniform over the cluster
     const float nan = __int_as_float(0x7fc00000);
     if (c.act && c.isx) {
       *reinterpret_cast<float2*>(gx_out) = make_float2(nan, nan);
@@ -603,32 +636,55 @@ __global__ void __launch_bounds__(256, ROLLED ? 2 : 1) kdot_small_fast_kernel(Si
       prm.valid[img] = status;
       if (prm.nits_per_img) prm.nits_per_img[img] = nits;
     }
-    if (split > 1) cluster.sync();  // no CTA of the cluster exits while a peer may still read its box
+    cluster.barrier_wait();
+    if (store_norm) *reinterpret_cast<float2*>(base + 2 * gidx) = vnorm;
     return;
   }
 
   dbg_stamp(prm, img, 3);
   // ---- stage this slot's columns: [student | pad | teacher | pad], pads carry h = -big (exp2 -> 0) ----
+  // The float64 squared distances come first: the columns' coordinates are parked as doubles in the second h buffer
+  // (not read before round 0 publishes into it), so the table costs two broadcast LDS.64, three DP operations and one
+  // STS.64 per column -- no fp32 -> fp64 conversions (XU pipe) in the loop.
+  double* cxd = c.hbd + 2 * kFastMaxCols;
+  double* cyd = c.hbd + 3 * kFastMaxCols;
   for (int j = lane; j < kFastMaxCols; j += 32) {
     c.cx[j] = 0.f; c.cy[j] = 0.f;
+    cxd[j] = 0.0; cyd[j] = 0.0;
+  }
+  if (lane < 4) c.ctr[lane] = 0.0;   // round 0 publishes uncentred offsets (potentials start at 0)
+  __syncwarp();
+  const double pxd = (double)c.px, pyd = (double)c.py;
+  if (c.act) {
+    c.cx[c.col] = c.px; c.cy[c.col] = c.py;
+    cxd[c.col] = pxd; cyd[c.col] = pyd;
+  }
+  __syncwarp();
+  {  // pads: columns at the origin, h = -big
+    const int ncol = Nq + Mq;  // multiple of 4
+#pragma unroll 2
+    for (int j = 0; j < ncol; j += 4) {
+      const double2 X0 = *reinterpret_cast<const double2*>(cxd + j), X1 = *reinterpret_cast<const double2*>(cxd + j + 2);
+      const double2 Y0 = *reinterpret_cast<const double2*>(cyd + j), Y1 = *reinterpret_cast<const double2*>(cyd + j + 2);
+      const double ax0 = X0.x - pxd, ax1 = X0.y - pxd, ax2 = X1.x - pxd, ax3 = X1.y - pxd;
+      const double ay0 = Y0.x - pyd, ay1 = Y0.y - pyd, ay2 = Y1.x - pyd, ay3 = Y1.y - pyd;
+      c.d2s[(j + 0) * 32] = fma(ay0, ay0, ax0 * ax0);
+      c.d2s[(j + 1) * 32] = fma(ay1, ay1, ax1 * ax1);
+      c.d2s[(j + 2) * 32] = fma(ay2, ay2, ax2 * ax2);
+      c.d2s[(j + 3) * 32] = fma(ay3, ay3, ax3 * ax3);
+    }
+  }
+  __syncwarp();
+  for (int j = lane; j < kFastMaxCols; j += 32) {
 #pragma unroll
     for (int v = 0; v < 4; ++v) { c.hb[v * kFastMaxCols + j] = kNegBig; c.hbd[v * kFastMaxCols + j] = (double)kNegBig; }
   }
   __syncwarp();
   if (c.act) {
-    c.cx[c.col] = c.px; c.cy[c.col] = c.py;
     c.hb[c.col] = c.lw2; c.hb[kFastMaxCols + c.col] = c.lw2;  // init round: h = log w for both views
     c.hbd[c.col] = c.lw2d; c.hbd[kFastMaxCols + c.col] = c.lw2d;
   }
   __syncwarp();
-
-  {  // float64 squared distances of this lane's point to every staged column (pads: columns at the origin, h = -big)
-    const double pxd = (double)c.px, pyd = (double)c.py;
-    for (int j = 0; j < Nq + Mq; ++j) {
-      const double ax = (double)c.cx[j] - pxd, ay = (double)c.cy[j] - pyd;
-      c.d2s[j * 32] = fma(ay, ay, ax * ax);
-    }
-  }
   double S = 0.0, C = 0.0;
   float gSx = 0.f, gSy = 0.f, gCx = 0.f, gCy = 0.f;
   RoundConst rc;
@@ -649,8 +705,8 @@ __global__ void __launch_bounds__(256, ROLLED ? 2 : 1) kdot_small_fast_kernel(Si
   dbg_stamp(prm, img, 5);
   // ---- loss + analytic backward ----
   const double rho = prm.rho;
-  const float lam = rho < 0.0 ? 1.f : (float)(1.0 / (1.0 + (double)rc.eps / rho));
-  const float gfac = rho < 0.0 ? 1.f : (float)((rho + 0.5 * (double)rc.eps) / rho) * lam;
+  // (rho + eps/2) / rho * lambda with lambda = 1 / (1 + eps/rho): one division
+  const float gfac = rho < 0.0 ? 1.f : (float)((rho + 0.5 * (double)rc.eps) / (rho + (double)rc.eps));
   double loss = 0.0;
   if (c.act) {
     const RowFinal f = row_final(S, C, rho, rc.eps);
@@ -667,12 +723,15 @@ __global__ void __launch_bounds__(256, ROLLED ? 2 : 1) kdot_small_fast_kernel(Si
     }
   }
   loss = warp_sum(loss);
+  cluster.barrier_wait();   // completes the arrive of the prologue (long done): every CTA of the cluster is running and has
+                            // read its raw points -> its shared memory may be written, the caller's buffer normalised
+  if (store_norm) *reinterpret_cast<float2*>(base + 2 * gidx) = vnorm;
   if (lane == 0) {
     double* dst = split > 1 ? cluster.map_shared_rank(s_slot_loss, 0) : s_slot_loss;  // rank 0 collects
     dst[slot] = loss;
     if (prm.loss_per_slot) prm.loss_per_slot[(size_t)img * B + slot] = (float)loss;
   }
-  if (split > 1) cluster.sync(); else __syncthreads();
+  cluster.sync();
   if (threadIdx.x == 0 && part == 0) {
     double tot = 0.0;
     for (int s = 0; s < B; ++s) tot += s_slot_loss[s];  // fixed order: deterministic

@@ -42,10 +42,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--scaling", type=float, default=0.5)
+    ap.add_argument("--cases", default="", help="only the cases whose name contains this substring")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     rows = []
     for name, kw in CASES:
+        if args.cases not in name:
+            continue
         b = ot_batch(**kw)
         xs, xt = torch.from_numpy(b["xs"]).to(dev), torch.from_numpy(b["xt"]).to(dev)
         ws, wt = torch.from_numpy(b["ws"]).to(dev), torch.from_numpy(b["wt"]).to(dev)

@@ -41,7 +41,7 @@ ts = []
 for i in range(30):
     torch.cuda._sleep(100000); e0.record(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) * 1e3)
 print("event pair alone: %.2f us" % np.median(ts))
-for nimg in (1, 64, 148, 512):
+for nimg in (() if os.environ.get('MB_QUICK') else (1, 64, 148, 512)):
     for scaling in (0.5, 0.05, 0.9):
         for cold in (False, True):
             us, ni = run(nimg, scaling, cold)
@@ -85,3 +85,13 @@ for n in (1, 10, 100):
     for _ in range(n): step(0)
     e1.record(); torch.cuda.synchronize()
     print("back-to-back x%d (queued behind a sleep): %.2f us per launch" % (n, e0.elapsed_time(e1) * 1e3 / n))
+if c[:, 8:].any():  # built with -DKDOT_SMALL_ROUND_STAMPS: clock at the start of rounds 0..7 (thread 0 of part 0)
+    print("cycles per round (7 stamped rounds, median over images):", np.median(np.diff(c[:, 8:16], axis=1), axis=0))
+    print("  last stamp -> end of the round phase (stamp 5):", np.median(c[:, 5] - c[:, 15]))
+# which CTAs finish last?  (the launch lasts as long as its slowest cluster)
+bb = ot_batch(64, seed=1, n_range=(8, 12), m_range=(8, 12))
+tot = c[:, 6] - c[:, 0]
+order = np.argsort(-tot)[:8]
+print("slowest images: (cycles, N, M)", [(int(tot[i]), bb["pos_per_img"][i], bb["pos_per_img_t"][i]) for i in order])
+order = np.argsort(tot)[:4]
+print("fastest images: (cycles, N, M)", [(int(tot[i]), bb["pos_per_img"][i], bb["pos_per_img_t"][i]) for i in order])
