@@ -214,7 +214,7 @@ template <int D>
 __host__ __device__ constexpr int stream_tile_cols() { return D <= 4 ? 128 : (D <= 8 ? 64 : 32); }
 // ... plus a float64 staging area for one 32-column sub-tile (D coordinates + h), see stream_subtile_hi
 template <int D>
-__host__ __device__ constexpr int stream_warp_smem_floats() { return 2 * (D + 1) * stream_tile_cols<D>() + 2 * (D + 1) * 32; }
+__host__ __device__ constexpr int stream_warp_smem_floats() { return 2 * (D + 1) * stream_tile_cols<D>() + 2 * (D + 1) * 32 + 8; }
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
   const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
@@ -257,14 +257,41 @@ constexpr float kSigThr = 1.0f / 16384.0f;
 #define KDOT_STREAM_HI_MAG 4096.0f
 #endif
 constexpr float kStreamHiMagnitude = KDOT_STREAM_HI_MAG;
+#ifndef KDOT_STREAM_HI_ROUNDS
+#define KDOT_STREAM_HI_ROUNDS KDOT_HI_ROUNDS
+#endif
+constexpr int kStreamHiRounds = KDOT_STREAM_HI_ROUNDS;  // trailing rounds that may take float64 sub-tiles
 
+// Arguments of the high-precision path.  They live in the warp's shared memory (the last 32 bytes of its region, written
+// by lane 0 before a sweep), not in registers: the kernel runs at 64 registers per thread for four CTAs per SM, and nine
+// registers held across the tile loop for a path that is taken by a few sub-tiles per sweep were spilled -- 89 M local
+// loads / stores per dense_b32 launch, 105 M sectors of write-through traffic to L2 (ncu, profiles/r02_prof_stream_*).
 struct HiArgs {
   const float* chlo;  // fp32 tail of h for the column set (same indexing as ch)
-  double* hsm;        // per-warp staging: [D + 1][32] float64
   double coefd;
-  float mag_fac;      // hi_mag_factor of this round: a sub-tile needs float64 arguments iff max|h| * mag_fac > 1
   long long* dbg;     // profiling aid (kdot_debug_set_clock_buffer): [5] screened, [6] float64 sub-tiles, [7] gradient-round float64 sub-tiles
+  float mag_fac;      // hi_mag_factor of this round: a sub-tile needs float64 arguments iff max|h| * mag_fac > 1
+  float pad;
 };
+static_assert(sizeof(HiArgs) == 32, "HiArgs occupies the 8 trailing floats of a warp's shared-memory region");
+
+template <int D>
+__device__ __forceinline__ HiArgs* stream_hi_args(float* wsm) {
+  return reinterpret_cast<HiArgs*>(wsm + 2 * (D + 1) * stream_tile_cols<D>() + 2 * (D + 1) * 32);
+}
+template <int D>
+__device__ __forceinline__ double* stream_hi_staging(float* wsm) {  // [D + 1][32] float64
+  return reinterpret_cast<double*>(wsm + 2 * (D + 1) * stream_tile_cols<D>());
+}
+template <int D>
+__device__ __forceinline__ void stream_hi_publish(float* wsm, int lane, const float* chlo, double coefd, float mag_fac, long long* dbg) {
+  __syncwarp();
+  if (lane == 0) {
+    HiArgs* ha = stream_hi_args<D>(wsm);
+    ha->chlo = chlo; ha->coefd = coefd; ha->dbg = dbg; ha->mag_fac = mag_fac; ha->pad = 0.f;
+  }
+  __syncwarp();
+}
 
 // Staging of one sub-tile for the float64 evaluation.  The argument is evaluated in the EXPANDED form
 //   u_ij = h_j + coef |x_j|^2  +  coef |p_i|^2 - ref_i  -  2 coef <x_j, p_i>        (exact enough in float64: 1e-10)
@@ -435,7 +462,7 @@ __device__ __forceinline__ void stream_subtile_hi(URow<D, R, GRAD> (&st)[R], dou
 template <int D, int R, bool GRAD, bool FOLD, bool P1, bool SEED, bool TSKIP, bool HI>
 __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const float* __restrict__ pts, int strideP,
                                             const float* ch, int ncols, float coef, float* wsm, int lane,
-                                            const TileSkip ts = TileSkip{}, const HiArgs ha = HiArgs{}) {
+                                            const TileSkip ts = TileSkip{}) {
   static_assert(!(HI && (FOLD || P1)), "high-precision sub-tiles exist for the unfolded squared cost only");
   static_assert(!TSKIP || (D == 2 && SEED), "tile skipping needs the D = 2 tile boxes and a seeded reference");
   constexpr int T = stream_tile_cols<D>();
@@ -503,7 +530,7 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
 #else
       constexpr bool kGradHi = true;
 #endif
-      if (kGradHi && HI && GRAD && subtile_hmag<D>(tb, T, sb, n, lane) * ha.mag_fac > 1.0f) {
+      if (kGradHi && HI && GRAD && subtile_hmag<D>(tb, T, sb, n, lane) * stream_hi_args<D>(wsm)->mag_fac > 1.0f) {
         // gradient round: float64 arguments for the sub-tiles that carry a visible share of a row's weights.  Screen with
         // a sums-only fp32 pass on copies (no state is touched); an overflow counts as "visible".
         URow<D, R, false> tmp[R];
@@ -528,10 +555,10 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
           sig |= !(gain <= kSigThr * fmaxf(st[k].s0 + gain, 1.0f));
         }
         grad_hi = __any_sync(0xffffffffu, sig);
-        if (ha.dbg && lane == 0) { atomicAdd((unsigned long long*)ha.dbg + 5, 1ull); if (grad_hi) atomicAdd((unsigned long long*)ha.dbg + 7, 1ull); }
+        if (lane == 0) if (long long* dbg = stream_hi_args<D>(wsm)->dbg) { atomicAdd((unsigned long long*)dbg + 5, 1ull); if (grad_hi) atomicAdd((unsigned long long*)dbg + 7, 1ull); }
       }
       if (HI && GRAD && grad_hi) {
-        stream_subtile_hi<D, R, GRAD>(st, ha.hsm, tb, T, sb, je - sb, lane, ha.chlo + t * T + sb, sb + lane < n, ha.coefd, inv_ncoef, big);
+        stream_subtile_hi<D, R, GRAD>(st, stream_hi_staging<D>(wsm), tb, T, sb, je - sb, lane, stream_hi_args<D>(wsm)->chlo + t * T + sb, sb + lane < n, stream_hi_args<D>(wsm)->coefd, inv_ncoef, big);
       } else {
         bool redo = true;
         if (!GRAD && !P1 && D <= 2) {  // speculate: whole sub-tile without overflow tests, one check at the end (larger D: registers)
@@ -576,11 +603,11 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
             const float sk = st[k].s.x + st[k].s.y;
             sig |= (sk - st[k].s0) > kSigThr * fmaxf(sk, 1.0f);
           }
-          if (__any_sync(0xffffffffu, sig) && subtile_hmag<D>(tb, T, sb, n, lane) * ha.mag_fac > 1.0f) {
-            if (ha.dbg && lane == 0) atomicAdd((unsigned long long*)ha.dbg + 6, 1ull);
+          if (__any_sync(0xffffffffu, sig) && subtile_hmag<D>(tb, T, sb, n, lane) * stream_hi_args<D>(wsm)->mag_fac > 1.0f) {
+            if (lane == 0) if (long long* dbg = stream_hi_args<D>(wsm)->dbg) atomicAdd((unsigned long long*)dbg + 6, 1ull);
 #pragma unroll
             for (int k = 0; k < R; ++k) st[k].s = make_float2(st[k].s0, 0.f);  // drop the fp32 contribution (s0 follows re-basing)
-            stream_subtile_hi<D, R, GRAD>(st, ha.hsm, tb, T, sb, je - sb, lane, ha.chlo + t * T + sb, sb + lane < n, ha.coefd, inv_ncoef, big);
+            stream_subtile_hi<D, R, GRAD>(st, stream_hi_staging<D>(wsm), tb, T, sb, je - sb, lane, stream_hi_args<D>(wsm)->chlo + t * T + sb, sb + lane < n, stream_hi_args<D>(wsm)->coefd, inv_ncoef, big);
           }
         }
       }
@@ -687,7 +714,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   double* pref = p.pref + (size_t)prob * 12;
   const double hmul_prev = r > 0 ? b.sched[(size_t)img * KDOT_MAX_ROUNDS + r - 1].hmuld : 0.0;
   unsigned int* hmag = p.hmag + (size_t)prob * 3;
-  const bool hi = !P1 && is_hi_round(r, nrounds, rc.eps, eps0) &&
+  const bool hi = !P1 && is_hi_round(r, nrounds, rc.eps, eps0, kStreamHiRounds) &&
                   __uint_as_float(__ldcg(hmag + r % 3)) * hi_mag_factor(r, nrounds) * (kHiMagnitude / kStreamHiMagnitude) > 1.0f;
   if (uu == 0 && lane == 0) hmag[(r + 2) % 3] = 0u;  // slot of round r + 2: last read in round r - 1, next written in round r + 1
   const double rho = b.rho;
@@ -711,11 +738,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   const float* hmCc = hmSc + ntile;
   float* hmSn = p.hmax + ((size_t)prob * 4 + (cur ^ 1) * 2) * ntile;
   float* hmCn = hmSn + ntile;
-  HiArgs ha{};
-  ha.hsm = reinterpret_cast<double*>(wsm + 2 * (D + 1) * T);
-  ha.coefd = rc.coefd;
-  ha.mag_fac = hi_mag_factor(r, nrounds) * (kHiMagnitude / kStreamHiMagnitude);
-  ha.dbg = b.dbg_clk;
+  const float hi_mag_fac = hi_mag_factor(r, nrounds) * (kHiMagnitude / kStreamHiMagnitude);
 
   if (last && rows_x) {
     if (!own) return;  // the student's last round is done by the "own" unit for both column sets
@@ -734,8 +757,8 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
         urow_seed<D, 1, true, P1>(st, pts, strideP, hSc, rc.coef, jb1);
         ts.tbox = tbox; ts.hmax = hmSc;
       }
-      ha.chlo = lSc;
-      if (hi) stream_rows<D, 1, true, false, P1, kSeed, kTSkip, !P1>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane, ts, ha);
+      if (hi) stream_hi_publish<D>(wsm, lane, lSc, rc.coefd, hi_mag_fac, b.dbg_clk);
+      if (hi) stream_rows<D, 1, true, false, P1, kSeed, kTSkip, !P1>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane, ts);
       else if (!warm) stream_rows<D, 1, true, false, P1, kSeed, kTSkip, false>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane, ts);
       else stream_rows<D, 1, true, false, P1, false, false, false>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane);
       const float sS = st[0].s.x + st[0].s.y;
@@ -749,8 +772,8 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
         urow_seed<D, 1, true, P1>(st, pts + p.nqMax, strideP, hCc + p.nqMax, rc.coef, jb1);
         ts.tbox = tbox + (p.nqMax >> 5); ts.hmax = hmCc + (p.nqMax >> 5);
       }
-      ha.chlo = lCc + p.nqMax;
-      if (hi) stream_rows<D, 1, true, false, P1, kSeed, kTSkip, !P1>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane, ts, ha);
+      if (hi) stream_hi_publish<D>(wsm, lane, lCc + p.nqMax, rc.coefd, hi_mag_fac, b.dbg_clk);
+      if (hi) stream_rows<D, 1, true, false, P1, kSeed, kTSkip, !P1>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane, ts);
       else if (!warm) stream_rows<D, 1, true, false, P1, kSeed, kTSkip, false>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane, ts);
       else stream_rows<D, 1, true, false, P1, false, false, false>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane);
       if (!act) continue;
@@ -807,8 +830,8 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
       ts.tbox = tbox + (coff >> 5);
       ts.hmax = (own ? hmSc : hmCc) + (coff >> 5);
     }
-    ha.chlo = (own ? lSc : lCc) + coff;
-    if (hi) stream_rows<D, R, false, false, P1, kSeed, kTSkip, !P1>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane, ts, ha);
+    if (hi) stream_hi_publish<D>(wsm, lane, (own ? lSc : lCc) + coff, rc.coefd, hi_mag_fac, b.dbg_clk);
+    if (hi) stream_rows<D, R, false, false, P1, kSeed, kTSkip, !P1>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane, ts);
     else stream_rows<D, R, false, false, P1, kSeed, kTSkip, false>(st, cpts, strideP, ch, ncols, rc.coef, wsm, lane, ts);
   }
   // new potentials / next round's h in float64; fp32 head + tail of h, per-tile maximum of the head (skip test)

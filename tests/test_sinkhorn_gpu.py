@@ -205,6 +205,29 @@ def test_stream_kernel_clouds_beyond_shared_memory():
     assert e_x <= parity.TOL_STREAM and q_x <= parity.TOL / 2
 
 
+def test_zebra_full_size_one_image():
+    """BASELINE.json configs[3] at FULL size (one of its 8 images): N = M = 4096 cells, D = 16 code probabilities,
+    blur 0.05, one slot -- the generic-dimension streaming kernel against the float64 oracle (4 x 4096^2 float64 cost
+    matrices, ~10 rounds: some tens of seconds of numpy)."""
+    from kd_6d_pose_adlp_b200.ops import OTConfig, ot_loss_batched
+    from kd_6d_pose_adlp_b200.synthetic import cu_seqlens
+    from oracle import sinkhorn_analytic
+
+    b = ot_batch(1, seed=16, dense=(4096, 4096), B=1, D=16)
+    dev = torch.device("cuda:0")
+    t = {k: torch.from_numpy(b[k]).to(dev) for k in ("xs", "ws", "xt", "wt")}
+    out = ot_loss_batched(t["xs"], t["ws"], t["xt"], t["wt"], b["pos_per_img"], b["pos_per_img_t"],
+                          OTConfig(blur=0.05), normalize=False)
+    torch.cuda.synchronize()
+    o = sinkhorn_analytic.kdot_fwd_bwd_f64(b["xs"], b["ws"], b["xt"], b["wt"], cu_seqlens(b["pos_per_img"]),
+                                           cu_seqlens(b["pos_per_img_t"]), 1, 16, blur=0.05, normalize=False)
+    assert np.array_equal(out["nits"].cpu().numpy(), o["nits"])
+    e_l, e_w = parity.rel(out["loss_per_img"].cpu().numpy(), o["loss_per_img"]), parity.rel(out["grad_ws"].cpu().numpy(), o["grad_ws"])
+    e_x = parity.rel(out["grad_xs"].cpu().numpy(), o["grad_xs"])
+    print(f"\nzebra 4096 x 4096, D = 16: loss {e_l:.2e} d/dalpha {e_w:.2e} d/dx {e_x:.2e}")
+    assert e_l <= parity.TOL and e_w <= parity.TOL and e_x <= parity.TOL
+
+
 @pytest.mark.parametrize("D,blur", [(16, 0.05), (16, 0.01), (3, 0.01), (8, 0.001)])
 def test_stream_kernel_generic_dimension(D, blur):
     """ZebraPose-style per-cell code distributions (BASELINE.json configs[3]): D-dimensional points, one slot."""
