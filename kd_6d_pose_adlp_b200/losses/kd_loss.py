@@ -227,7 +227,7 @@ def make_kd_pose_loss(base):
                 if self.weighted_ot:
                     self.pred_cls = torch.clamp(torch.sigmoid(flatten_level_list(pred_cls)[pos_inds]), min=10e-4, max=1 - 10e-4)
                 self.cls_id = torch.unique(cls_label)
-                cell = pos_inds - torch.div(pos_inds, res["cells"], rounding_mode="floor") * res["cells"]
+                cell = torch.remainder(pos_inds, res["cells"])
                 pred_xy = gather_decode(pred_reg, pos_inds, cls_label, anchors_one[cell], bt_pos)
                 reg_loss, kd_loss = self._losses_from_keypoints(pred_xy, aux_3d_pos, cls_label, pred_t)
             else:

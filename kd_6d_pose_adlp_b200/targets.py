@@ -29,8 +29,9 @@ MAX_GT = 8
 
 
 def _stack_targets(targets, dev):
-    """Per-image object lists padded to ``maxgt`` (<= 8) and stacked -- a dozen launches for the whole mini-batch (one
-    ``cat`` / ``stack`` per field and one scatter into the padded layout), independent of the number of images."""
+    """Per-image object lists padded to ``maxgt`` (<= 8) and stacked -- a handful of launches for the whole mini-batch
+    (one ``cat`` / ``stack`` per field, one gather into the padded layout; none at all for the padding when every image
+    holds the same number of objects), independent of the number of images."""
     nimg = len(targets)
     ngt = [int(t.class_ids.shape[0]) for t in targets]
     maxgt = max(1, max(ngt))
@@ -38,32 +39,44 @@ def _stack_targets(targets, dev):
         raise ValueError(f"kdot_ssc_count handles up to {MAX_GT} objects per image, got {maxgt}")
     f32 = dict(dtype=torch.float32, device=dev)
     with_obj = [t for t, g in zip(targets, ngt) if g > 0]
-    rot = torch.zeros(nimg, maxgt, 3, 3, **f32)
-    trans = torch.zeros(nimg, maxgt, 3, **f32)
-    kp3d = torch.zeros(nimg, maxgt, 8, 3, **f32)
-    cls1 = torch.zeros(nimg, maxgt, dtype=torch.int64, device=dev)
     if with_obj:
-        ids = torch.cat([t.class_ids.reshape(-1) for t in with_obj]).to(dev).long()
-        rflat = torch.cat([t.rotations.reshape(-1, 3, 3) for t in with_obj]).to(**f32)
-        tflat = torch.cat([t.translations.reshape(-1, 3) for t in with_obj]).to(**f32)
-        shared = all(t.keypoints_3d is with_obj[0].keypoints_3d for t in with_obj)
-        if shared:
-            kflat = with_obj[0].keypoints_3d.to(**f32)[ids]
+        ids = torch.cat([t.class_ids for t in with_obj]).reshape(-1).to(dev).long()
+        rflat = torch.cat([t.rotations for t in with_obj]).reshape(-1, 3, 3).to(**f32)
+        tflat = torch.cat([t.translations for t in with_obj]).reshape(-1, 3).to(**f32)
+        kp0 = with_obj[0].keypoints_3d
+        if all(t.keypoints_3d is kp0 for t in with_obj):
+            kflat = kp0.to(**f32)[ids]
         else:
             kflat = torch.cat([t.keypoints_3d.to(**f32)[t.class_ids.to(dev).long()] for t in with_obj])
-        where = np.asarray([(i, g) for i, n in enumerate(ngt) for g in range(n)], np.int64)
-        idx = torch.from_numpy(where).to(dev, non_blocking=True)
-        ii, gg = idx[:, 0], idx[:, 1]
-        rot[ii, gg], trans[ii, gg], kp3d[ii, gg], cls1[ii, gg] = rflat, tflat, kflat, ids + 1
+        if min(ngt) == maxgt:      # no padding needed: the flat arrays ARE the padded layout
+            rot, trans = rflat.view(nimg, maxgt, 3, 3), tflat.view(nimg, maxgt, 3)
+            kp3d, cls1 = kflat.view(nimg, maxgt, 8, 3), (ids + 1).view(nimg, maxgt)
+        else:                      # gather through an index with a sentinel row of zeros appended to every flat array
+            total = int(ids.shape[0])
+            where = np.full((nimg, maxgt), total, np.int64)
+            o = 0
+            for i, n in enumerate(ngt):
+                where[i, :n] = np.arange(o, o + n)
+                o += n
+            idx = torch.from_numpy(where.reshape(-1)).to(dev, non_blocking=True)
+            pad = lambda a: torch.cat([a, a.new_zeros((1,) + tuple(a.shape[1:]))])[idx]
+            rot, trans = pad(rflat).view(nimg, maxgt, 3, 3), pad(tflat).view(nimg, maxgt, 3)
+            kp3d, cls1 = pad(kflat).view(nimg, maxgt, 8, 3), pad(ids + 1).view(nimg, maxgt)
+    else:
+        rot = torch.zeros(nimg, maxgt, 3, 3, **f32)
+        trans = torch.zeros(nimg, maxgt, 3, **f32)
+        kp3d = torch.zeros(nimg, maxgt, 8, 3, **f32)
+        cls1 = torch.zeros(nimg, maxgt, dtype=torch.int64, device=dev)
     mask = torch.stack([t.mask for t in targets]).to(**f32)
     same_k = all(t.K is targets[0].K for t in targets)
     K = (targets[0].K.to(**f32).view(1, 3, 3).expand(nimg, 3, 3).contiguous() if same_k
-         else torch.stack([t.K.reshape(3, 3) for t in targets]).to(**f32))
+         else torch.stack([t.K for t in targets]).reshape(nimg, 3, 3).to(**f32))
     has_bt = [getattr(t, "bbox_trans", None) is not None for t in targets]
     if any(has_bt) and not all(has_bt):
         raise ValueError("either every target carries bbox_trans or none does")
-    bt = torch.stack([t.bbox_trans.reshape(2, 3) for t in targets]).to(**f32) if all(has_bt) else None
-    return dict(nimg=nimg, ngt=ngt, maxgt=maxgt, rot=rot, trans=trans, kp3d=kp3d, cls1=cls1, mask=mask.contiguous(), K=K, bt=bt,
+    bt = torch.stack([t.bbox_trans for t in targets]).reshape(nimg, 2, 3).to(**f32) if all(has_bt) else None
+    return dict(nimg=nimg, ngt=ngt, maxgt=maxgt, rot=rot.contiguous(), trans=trans.contiguous(), kp3d=kp3d.contiguous(),
+                cls1=cls1.contiguous(), mask=mask.contiguous(), K=K, bt=bt,
                 num_gt=torch.tensor(ngt, dtype=torch.int32).to(dev, non_blocking=True))
 
 
@@ -135,9 +148,10 @@ def positives_aux(res, pos_inds: torch.Tensor):
     the 3-D key-points in the camera frame ``R X + T`` ``(npos, 8, 3)`` and the crop affine ``(npos, 2, 3)``."""
     st, cells = res["st"], res["cells"]
     img = torch.div(pos_inds, cells, rounding_mode="floor")
-    g = res["owner"][pos_inds].long()
-    cls_label = st["cls1"][img, g] - 1
-    R, T, X = st["rot"][img, g], st["trans"][img, g], st["kp3d"][img, g]
-    aux_3d = torch.baddbmm(T.unsqueeze(1), X, R.transpose(1, 2))            # (R X^T + T)^T
+    slot = img * st["maxgt"] + res["owner"][pos_inds]                        # row of the padded (image, object) tables
+    cls_label = st["cls1"].view(-1)[slot] - 1
+    # camera-frame key-points of every (image, object) once -- (R X^T + T)^T, one batched product -- then one gather
+    cam = torch.baddbmm(st["trans"].view(-1, 1, 3), st["kp3d"].view(-1, 8, 3), st["rot"].view(-1, 3, 3).transpose(1, 2))
+    aux_3d = cam[slot]
     bt = None if st["bt"] is None else st["bt"][img]
     return cls_label, aux_3d, bt

@@ -62,6 +62,17 @@ def main():
         torch.cuda.synchronize()
         ts.append((time.perf_counter() - t0) * 1e3)
     print("median ms/step", sorted(ts)[len(ts) // 2])
+    if os.environ.get("KDOT_CPROFILE"):
+        import cProfile, pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+        pr.disable()
+        st = pstats.Stats(pr)
+        st.sort_stats("cumulative").print_stats(45)
+        return
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         for _ in range(5):
             step()
