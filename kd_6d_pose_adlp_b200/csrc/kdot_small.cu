@@ -311,6 +311,7 @@ __device__ __forceinline__ void fast_solve(const FastCtx& c, int nrounds, const 
     // the end of the previous round: two broadcast LDS.128 instead of eight shuffles (330 cycles per round, measured)
     const double2 own = *reinterpret_cast<const double2*>(c.ctr + (c.isx ? 0 : 2));   // this lane's own set
     const double2 oth = *reinterpret_cast<const double2*>(c.ctr + (c.isx ? 2 : 0));
+    __syncwarp();   // every lane holds the centres before lanes 0 / N overwrite them at the end of this round
     const double ownS = own.x, ownC = own.y;
     const double refX = c.isx ? own.x : oth.y;   // student columns: student rows read h^S[X], teacher rows h^C[X]
     const double refY = c.isx ? oth.y : own.x;   // teacher columns: student rows read h^C[Y], teacher rows h^S[Y]
@@ -419,6 +420,7 @@ __device__ __forceinline__ void fast_solve_rt(const FastCtx& c, int nch, int nro
     // the end of the previous round: two broadcast LDS.128 instead of eight shuffles
     const double2 own = *reinterpret_cast<const double2*>(c.ctr + (c.isx ? 0 : 2));   // this lane's own set
     const double2 oth = *reinterpret_cast<const double2*>(c.ctr + (c.isx ? 2 : 0));
+    __syncwarp();   // every lane holds the centres before lanes 0 / N overwrite them at the end of this round
     const double ownS = own.x, ownC = own.y;
     const double refX = c.isx ? own.x : oth.y;   // student columns: student rows read h^S[X], teacher rows h^C[X]
     const double refY = c.isx ? oth.y : own.x;   // teacher columns: student rows read h^C[Y], teacher rows h^S[Y]
