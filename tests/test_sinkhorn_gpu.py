@@ -53,6 +53,28 @@ def test_small_kernel_ape_shape(nimg, sigma):
     check(ot_batch(nimg, seed=nimg, sigma=sigma))
 
 
+@pytest.mark.parametrize("B", [1, 2, 4, 16])
+@pytest.mark.parametrize("nimg", [3, 200])
+def test_small_kernel_slot_counts(B, nimg):
+    """Slot counts other than the 8 key-points of the reference (B = 16: two CTAs per image at least; nimg = 200: more
+    CTAs than SMs, the rolled variant): every warp derives the image-wide bounding box from the raw points of all B
+    slots, and the in-place normalisation waits for the whole cluster -- diameter (hence `nits`), normalised
+    coordinates and gradients have to match for every split."""
+    from kd_6d_pose_adlp_b200.synthetic import cu_seqlens
+    from oracle import sinkhorn_analytic
+
+    b = ot_batch(nimg, seed=10 * B + nimg, B=B, p_empty_teacher=0.2)
+    g = run_gpu(b)
+    o = sinkhorn_analytic.kdot_fwd_bwd_f64(b["xs"], b["ws"], b["xt"], b["wt"], cu_seqlens(b["pos_per_img"]),
+                                           cu_seqlens(b["pos_per_img_t"]), B, 2)
+    np.testing.assert_array_equal(g["valid"], o["valid"])
+    np.testing.assert_array_equal(g["nits"], o["nits"])
+    np.testing.assert_array_equal(g["xs_norm"], o["xs_norm"])   # in-place side effect, bit-exact
+    np.testing.assert_array_equal(g["xt_norm"], o["xt_norm"])
+    for name in ("loss_per_img", "grad_xs", "grad_ws"):
+        assert parity.rel(g[name], o[name]) <= parity.TOL, (name, parity.rel(g[name], o[name]))
+
+
 def test_small_kernel_up_to_64_points():
     check(ot_batch(5, seed=3, n_range=(20, 32), m_range=(20, 32)))
 
