@@ -41,8 +41,11 @@ struct RoundConst {
 // float64 -- but only while they are COLD (eps < eps_0 / 256): in a warm round |coef * d^2| <= 0.72 * eps_0 / eps < 185
 // log2-units, where an fp32 argument is accurate to ~1e-5 anyway.  Errors made in earlier rounds are halved by every
 // averaged update that follows, so six trailing rounds leave less than 2^-6 of an fp32 potential's rounding error.
+#ifndef KDOT_HI_EPS_RATIO
+#define KDOT_HI_EPS_RATIO 256.0f
+#endif
 __device__ __forceinline__ bool is_hi_round(int r, int nrounds, float eps, float eps0, int last = KDOT_HI_ROUNDS) {
-  return r >= nrounds - last && eps * 256.0f < eps0;
+  return r >= nrounds - last && eps * KDOT_HI_EPS_RATIO < eps0;
 }
 
 // Magnitude test that goes with is_hi_round: an fp32 soft-min argument carries an error of ~2^-24 max(|h_j|, |coef d^2|),

@@ -67,14 +67,35 @@ struct URow {
   float nx[D];          // -p_i
   float mref;           // reference exponent of the running sums (may be stale by up to ~kTauS)
   float2 mu;            // mref / (-coef), duplicated: folded into the squared-distance FMA chain
-  float2 s;
+  float2 s;             // partial sums of the CURRENT 32-column sub-tile (two interleaved accumulators)
+  float tot, comp;      // compensated (Kahan) total of the finished sub-tiles, same scale; row sum = tot - comp
   float2 g[GRAD ? D : 1];
   // cold rounds (SKIP): the 32-column sub-tile that added the most to the running sum so far.  Its maximum is within a
   // factor 32 (5 log2 units) of the row maximum, so it seeds the next round's sweep (urow_seed) with a reference that
   // needs no re-basing and puts every far tile below the skip threshold from the first column on.
   int jb;
-  float gbest, s0;
+  float gbest;
 };
+
+// Row sums.  A row of a dense cloud adds up thousands of exponentials of comparable size in the early rounds; two
+// running fp32 accumulators lose ~sqrt(n) 2^-24 there (1e-6 at n = 1360), the potentials inherit eps_r times that, and
+// the last round divides what survives by eps_final = 1e-6: emulated in numpy, sequential fp32 row sums alone put 4e-3
+// into the final offsets and 4e-5..3e-4 into d/dx of the dense 1360 x 1364 problem, a compensated sum over 32-column
+// sub-tiles 2e-6 (float64 pair arguments and exact exponentials changed nothing -- DESIGN.md section 3).  So the fp32
+// accumulators only ever span one sub-tile (16 terms each) and are folded into a Kahan pair: 4 FADD per row and sub-tile.
+template <int D, int R, bool GRAD>
+__device__ __forceinline__ void urow_fold(URow<D, R, GRAD>& st) {
+  const float y = __fsub_rn(__fadd_rn(st.s.x, st.s.y), st.comp);
+  const float t = __fadd_rn(st.tot, y);
+  st.comp = __fsub_rn(__fsub_rn(t, st.tot), y);
+  st.tot = t;
+  st.s = make_float2(0.f, 0.f);
+}
+// log2 of the row sum tot - comp
+template <int D, int R, bool GRAD>
+__device__ __forceinline__ double urow_lg2_sum(const URow<D, R, GRAD>& st) {
+  return lg2_sum_exact(st.tot) - (st.tot > 0.f ? (double)__fdiv_rn(st.comp, st.tot) * 1.4426950408889634 : 0.0);
+}
 
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
@@ -156,7 +177,7 @@ __device__ __forceinline__ void stream_chunk(URow<D, R, GRAD> (&st)[R], const fl
       }
       st[k].mref = vm;
       st[k].gbest *= sc;   // the sub-tile bookkeeping of stream_rows lives on the same scale as the sums
-      st[k].s0 *= sc;
+      st[k].tot *= sc; st[k].comp *= sc;
       const float mu = vm * inv_ncoef;
       st[k].mu = make_float2(mu, mu);
       const float2 p0 = make_float2(ex2_approx(v0.x - vm), ex2_approx(v0.y - vm));
@@ -247,12 +268,15 @@ struct TileSkip {
 // per-warp buffer (coordinates are exact fp32 -> float64 conversions, h = fp32 head + fp32 tail read from L2).
 // What stays fp32 adds up to < 32 * kSigThr per row with ~1e-3 relative error each: < 1e-6 of the sum.
 // The gradient round evaluates every sub-tile it does not skip this way (its weights enter d/dx directly).
-constexpr float kSigThr = 1.0f / 16384.0f;
-// Stream-kernel value of kHiMagnitude (kdot_common.cuh).  Clouds of several hundred points and more: the max-norm of the
-// d/dx error is set by a few ill-conditioned cells (near-ties between neighbours) that react to the 2^-22 error of
-// ex2.approx itself -- 2e-5..1.7e-4 with or without float64 arguments (tools/accuracy_stream_scan.py, 16 streaming cases:
-// mean 4e-5 vs 6e-5) -- while the screened float64 sub-tiles cost dense_b32 12 %.  They are therefore reserved for
-// problems whose CENTRED offsets exceed 8192 log2-units in the last round (fp32 argument error > 5e-4: wide, sparse clouds).
+#ifndef KDOT_SIG_THR
+#define KDOT_SIG_THR (1.0f / 16384.0f)
+#endif
+constexpr float kSigThr = KDOT_SIG_THR;
+// Stream-kernel value of kHiMagnitude (kdot_common.cuh).  With the compensated row sums (urow_fold) in place the fp32
+// pair arguments are what is left: tools/accuracy_stream_scan.py (16 streaming cases, max-norm of d/dx against float64)
+// gives 1.4e-4 / 1.1e-4 / 8.6e-5 at a gate of 4096 / 512 / 64 log2-units of CENTRED offset magnitude -- the maximum is set
+// by the wide, sparse clouds (sigma = 0.3) -- for 8.43 / 8.64 / 8.82 ms on dense_b32, whose own max-norm (1.1e-4) is ONE
+// knife-edge cell of 21 760 that sits at 1.0e-4..1.1e-4 even with float64 arguments everywhere (99.9 % quantile: 2e-6).
 #ifndef KDOT_STREAM_HI_MAG
 #define KDOT_STREAM_HI_MAG 4096.0f
 #endif
@@ -389,8 +413,13 @@ __device__ __noinline__ HiIO<D, R, GRAD> subtile_hi(HiIO<D, R, GRAD> io, double*
     }
 #pragma unroll
     for (int k = 0; k < R; ++k) {
+#ifdef KDOT_HI_EXACT_EXP   // experiment: correctly rounded exponentials in the float64 sub-tiles
+      float p0 = (float)exp2(u[k][0]), p1 = (float)exp2(u[k][1]);
+      float p2 = (float)exp2(u[k][2]), p3 = (float)exp2(u[k][3]);
+#else
       float p0 = ex2_approx(hi_pack(u[k][0])), p1 = ex2_approx(hi_pack(u[k][1]));
       float p2 = ex2_approx(hi_pack(u[k][2])), p3 = ex2_approx((float)u[k][3]);
+#endif
       if (!((p0 + p1) + (p2 + p3) <= big)) {  // cold: re-base on the max of this chunk
         const float um = (float)fmax(fmax(u[k][0], u[k][1]), fmax(u[k][2], u[k][3]));  // relative to the old reference
         const float vm = io.mref[k] + um;                                                  // any fp32 number near the max will do
@@ -404,8 +433,13 @@ __device__ __noinline__ HiIO<D, R, GRAD> subtile_hi(HiIO<D, R, GRAD> io, double*
         io.mref[k] = vm;
         io.sc[k] *= sc;
         K[k] -= shift;
+#ifdef KDOT_HI_EXACT_EXP
+        p0 = (float)exp2(u[k][0] - shift); p1 = (float)exp2(u[k][1] - shift);
+        p2 = (float)exp2(u[k][2] - shift); p3 = (float)exp2(u[k][3] - shift);
+#else
         p0 = ex2_approx(hi_pack(u[k][0] - shift)); p1 = ex2_approx(hi_pack(u[k][1] - shift));
         p2 = ex2_approx(hi_pack(u[k][2] - shift)); p3 = ex2_approx((float)(u[k][3] - shift));
+#endif
       }
       io.s[k].x += p0 + p2; io.s[k].y += p1 + p3;
       if (GRAD) {  // weights from the float64 argument, coordinate differences in fp32 (exact enough: they are O(cloud size))
@@ -450,7 +484,7 @@ __device__ __forceinline__ void stream_subtile_hi(URow<D, R, GRAD> (&st)[R], dou
     if (io.mref[k] != st[k].mref) {
       st[k].mref = io.mref[k];
       st[k].gbest *= io.sc[k];
-      st[k].s0 *= io.sc[k];
+      st[k].tot *= io.sc[k]; st[k].comp *= io.sc[k];
       const float mu = io.mref[k] * inv_ncoef;
       st[k].mu = make_float2(mu, mu);
     }
@@ -519,11 +553,7 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
 #pragma unroll 1
     for (int sb = 0; sb < n; sb += 32) {
       if (TSKIP && ((dead >> (sb >> 5)) & 1u)) continue;
-      if (SEED || HI) {
-#pragma unroll
-        for (int k = 0; k < R; ++k) st[k].s0 = st[k].s.x + st[k].s.y;
-      }
-      const int je = min(sb + 32, n);
+      const int je = min(sb + 32, n);   // st[k].s == 0 here: the previous sub-tile was folded into (tot, comp)
       bool grad_hi = false;
 #ifdef KDOT_NO_GRAD_HI
       constexpr bool kGradHi = false;
@@ -552,7 +582,7 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
 #pragma unroll
         for (int k = 0; k < R; ++k) {
           const float gain = tmp[k].s.x + tmp[k].s.y;
-          sig |= !(gain <= kSigThr * fmaxf(st[k].s0 + gain, 1.0f));
+          sig |= !(gain <= kSigThr * fmaxf(st[k].tot + gain, 1.0f));
         }
         grad_hi = __any_sync(0xffffffffu, sig);
         if (lane == 0) if (long long* dbg = stream_hi_args<D>(wsm)->dbg) { atomicAdd((unsigned long long*)dbg + 5, 1ull); if (grad_hi) atomicAdd((unsigned long long*)dbg + 7, 1ull); }
@@ -562,9 +592,6 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
       } else {
         bool redo = true;
         if (!GRAD && !P1 && D <= 2) {  // speculate: whole sub-tile without overflow tests, one check at the end (larger D: registers)
-          float2 sv[R];
-#pragma unroll
-          for (int k = 0; k < R; ++k) sv[k] = st[k].s;
 #pragma unroll 4
           for (int j = sb; j < je; j += 4) {
             float4 X[D];
@@ -578,7 +605,7 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
           for (int k = 0; k < R; ++k) redo |= !(st[k].s.x + st[k].s.y <= big);
           if (redo) {
 #pragma unroll
-            for (int k = 0; k < R; ++k) st[k].s = sv[k];
+            for (int k = 0; k < R; ++k) st[k].s = make_float2(0.f, 0.f);
           }
         }
         if (redo) {
@@ -600,13 +627,13 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
           bool sig = false;
 #pragma unroll
           for (int k = 0; k < R; ++k) {
-            const float sk = st[k].s.x + st[k].s.y;
-            sig |= (sk - st[k].s0) > kSigThr * fmaxf(sk, 1.0f);
+            const float gain = st[k].s.x + st[k].s.y;
+            sig |= gain > kSigThr * fmaxf(st[k].tot + gain, 1.0f);
           }
           if (__any_sync(0xffffffffu, sig) && subtile_hmag<D>(tb, T, sb, n, lane) * stream_hi_args<D>(wsm)->mag_fac > 1.0f) {
             if (lane == 0) if (long long* dbg = stream_hi_args<D>(wsm)->dbg) atomicAdd((unsigned long long*)dbg + 6, 1ull);
 #pragma unroll
-            for (int k = 0; k < R; ++k) st[k].s = make_float2(st[k].s0, 0.f);  // drop the fp32 contribution (s0 follows re-basing)
+            for (int k = 0; k < R; ++k) st[k].s = make_float2(0.f, 0.f);  // drop the fp32 contribution
             stream_subtile_hi<D, R, GRAD>(st, stream_hi_staging<D>(wsm), tb, T, sb, je - sb, lane, stream_hi_args<D>(wsm)->chlo + t * T + sb, sb + lane < n, stream_hi_args<D>(wsm)->coefd, inv_ncoef, big);
           }
         }
@@ -614,10 +641,12 @@ __device__ __forceinline__ void stream_rows(URow<D, R, GRAD> (&st)[R], const flo
       if (SEED) {
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-          const float gain = (st[k].s.x + st[k].s.y) - st[k].s0;
+          const float gain = st[k].s.x + st[k].s.y;
           if (gain > st[k].gbest) { st[k].gbest = gain; st[k].jb = t * T + sb; }
         }
       }
+#pragma unroll
+      for (int k = 0; k < R; ++k) urow_fold(st[k]);
     }
     __syncwarp();  // every lane is done with this buffer before tile t+2 overwrites it
   }
@@ -630,7 +659,7 @@ __device__ __forceinline__ void urow_reset(URow<D, R, GRAD> (&st)[R], float inv_
     st[k].mref = kNegBig;
     st[k].jb = 0;
     st[k].gbest = 0.f;
-    st[k].s0 = 0.f;
+    st[k].tot = 0.f; st[k].comp = 0.f;
     st[k].mu = make_float2(kNegBig * inv_ncoef, kNegBig * inv_ncoef);
     st[k].s = make_float2(0.f, 0.f);
 #pragma unroll
@@ -761,8 +790,8 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
       if (hi) stream_rows<D, 1, true, false, P1, kSeed, kTSkip, !P1>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane, ts);
       else if (!warm) stream_rows<D, 1, true, false, P1, kSeed, kTSkip, false>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane, ts);
       else stream_rows<D, 1, true, false, P1, false, false, false>(st, pts, strideP, hSc, Nq, rc.coef, wsm, lane);
-      const float sS = st[0].s.x + st[0].s.y;
-      const double S = rc.scaled * ((double)st[0].mref + lg2_sum_exact(sS) + __ldcg(pref + (r % 3) * 4 + 0) * hmul_prev);  // type S, cloud X
+      const float sS = st[0].tot;
+      const double S = rc.scaled * ((double)st[0].mref + urow_lg2_sum(st[0]) + __ldcg(pref + (r % 3) * 4 + 0) * hmul_prev);  // type S, cloud X
       float gS[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) gS[d] = (st[0].g[d].x + st[0].g[d].y) / sS;
@@ -777,8 +806,8 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
       else if (!warm) stream_rows<D, 1, true, false, P1, kSeed, kTSkip, false>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane, ts);
       else stream_rows<D, 1, true, false, P1, false, false, false>(st, pts + p.nqMax, strideP, hCc + p.nqMax, Mq, rc.coef, wsm, lane);
       if (!act) continue;
-      const float sC = st[0].s.x + st[0].s.y;
-      const double C = rc.scaled * ((double)st[0].mref + lg2_sum_exact(sC) + __ldcg(pref + (r % 3) * 4 + 3) * hmul_prev);  // type C, cloud Y
+      const float sC = st[0].tot;
+      const double C = rc.scaled * ((double)st[0].mref + urow_lg2_sum(st[0]) + __ldcg(pref + (r % 3) * 4 + 3) * hmul_prev);  // type C, cloud Y
       const RowFinal f = row_final(S, C, rho, rc.eps);
       const float lam = rho < 0.0 ? 1.f : (float)(1.0 / (1.0 + (double)rc.eps / rho));
       const float gfac = rho < 0.0 ? 1.f : (float)((rho + 0.5 * (double)rc.eps) / rho) * lam;
@@ -846,7 +875,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
     // warm rounds fold the reference into the distance chain as mu = fl(mref / -coef): the sums are relative to
     // -coef * mu, which differs from mref by the rounding of mu (6e-8 |mref|: up to 1e-5) -- add back what was subtracted
     const double ref = warm ? -(double)rc.coef * (double)st[k].mu.x : (double)st[k].mref;
-    const double lse = ref + lg2_sum_exact(st[k].s.x + st[k].s.y) + c_in;
+    const double lse = ref + urow_lg2_sum(st[k]) + c_in;
     double* pot = own ? potS : potC;
     const double nv = rc.scaled * lse;
     const double pv = (r == 0 || last) ? nv : 0.5 * (__ldcg(pot + ridx[k]) + nv);
