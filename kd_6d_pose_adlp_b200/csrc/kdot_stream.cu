@@ -281,6 +281,14 @@ constexpr float kSigThr = KDOT_SIG_THR;
 #define KDOT_STREAM_HI_MAG 4096.0f
 #endif
 constexpr float kStreamHiMagnitude = KDOT_STREAM_HI_MAG;
+// Problems of up to kStreamSmallPoints staged points (both clouds) take the register / CTA-resident kernels' gate instead
+// (kHiMagnitude = 64): there the float64 sub-tiles cost next to nothing in absolute terms and bring the wide sparse clouds of
+// the scan from 1.4e-4 to <= 8.6e-5, while on dense_b32 (2752 staged points) the lower gate costs 4.6 % for one cell moving
+// from 1.14e-4 to 1.01e-4.
+#ifndef KDOT_STREAM_SMALL_POINTS
+#define KDOT_STREAM_SMALL_POINTS 2048
+#endif
+constexpr int kStreamSmallPoints = KDOT_STREAM_SMALL_POINTS;
 #ifndef KDOT_STREAM_HI_ROUNDS
 #define KDOT_STREAM_HI_ROUNDS KDOT_HI_ROUNDS
 #endif
@@ -731,9 +739,9 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   const RoundConst rc = b.sched[(size_t)img * KDOT_MAX_ROUNDS + r];
   const float eps0 = b.sched[(size_t)img * KDOT_MAX_ROUNDS].eps;
   const bool warm = !P1 && rc.eps * 256.0f >= eps0;   // reference exponent folded into the distance chain (one op less per pair)
-  // float64 pair arguments only for problems whose offsets are large enough for fp32 to hurt (kStreamHiMagnitude): the
-  // screened float64 sub-tiles cost the dense configurations ~12 % for no measurable gain in accuracy (their |h| stays
-  // in the hundreds), while sparse / wide clouds (|h| ~ 1e4) need them
+  // float64 pair arguments only for problems whose centred offsets are large enough for fp32 to hurt: above
+  // kStreamHiMagnitude log2-units for the large batches, above kHiMagnitude for clouds of up to kStreamSmallPoints points
+  const float gate_ratio = p.strideP <= kStreamSmallPoints ? 1.0f : kHiMagnitude / kStreamHiMagnitude;
   // Centred offsets.  Unbalanced OT with unequal total masses puts a common term of order rho * log(mass ratio) / eps
   // (1e4 log2-units at eps = 1e-6) into every potential of a cloud; it cancels in h_j - max_j, but an fp32 head of h
   // would spend its mantissa on it.  The h of every (type S/C, cloud X/Y) set is therefore published relative to
@@ -744,7 +752,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   const double hmul_prev = r > 0 ? b.sched[(size_t)img * KDOT_MAX_ROUNDS + r - 1].hmuld : 0.0;
   unsigned int* hmag = p.hmag + (size_t)prob * 3;
   const bool hi = !P1 && is_hi_round(r, nrounds, rc.eps, eps0, kStreamHiRounds) &&
-                  __uint_as_float(__ldcg(hmag + r % 3)) * hi_mag_factor(r, nrounds) * (kHiMagnitude / kStreamHiMagnitude) > 1.0f;
+                  __uint_as_float(__ldcg(hmag + r % 3)) * hi_mag_factor(r, nrounds) * gate_ratio > 1.0f;
   if (uu == 0 && lane == 0) hmag[(r + 2) % 3] = 0u;  // slot of round r + 2: last read in round r - 1, next written in round r + 1
   const double rho = b.rho;
   const float* pts = p.pts + (size_t)prob * D * strideP;
@@ -767,7 +775,7 @@ __device__ __forceinline__ void stream_unit(const StreamParams& p, int r, int pr
   const float* hmCc = hmSc + ntile;
   float* hmSn = p.hmax + ((size_t)prob * 4 + (cur ^ 1) * 2) * ntile;
   float* hmCn = hmSn + ntile;
-  const float hi_mag_fac = hi_mag_factor(r, nrounds) * (kHiMagnitude / kStreamHiMagnitude);
+  const float hi_mag_fac = hi_mag_factor(r, nrounds) * gate_ratio;
 
   if (last && rows_x) {
     if (!own) return;  // the student's last round is done by the "own" unit for both column sets
