@@ -421,13 +421,9 @@ __device__ __noinline__ HiIO<D, R, GRAD> subtile_hi(HiIO<D, R, GRAD> io, double*
     }
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-#ifdef KDOT_HI_EXACT_EXP   // experiment: correctly rounded exponentials in the float64 sub-tiles
-      float p0 = (float)exp2(u[k][0]), p1 = (float)exp2(u[k][1]);
-      float p2 = (float)exp2(u[k][2]), p3 = (float)exp2(u[k][3]);
-#else
+      // (correctly rounded exponentials here -- exp2() in float64 -- change no digit of the worst cases: DESIGN.md section 3)
       float p0 = ex2_approx(hi_pack(u[k][0])), p1 = ex2_approx(hi_pack(u[k][1]));
       float p2 = ex2_approx(hi_pack(u[k][2])), p3 = ex2_approx((float)u[k][3]);
-#endif
       if (!((p0 + p1) + (p2 + p3) <= big)) {  // cold: re-base on the max of this chunk
         const float um = (float)fmax(fmax(u[k][0], u[k][1]), fmax(u[k][2], u[k][3]));  // relative to the old reference
         const float vm = io.mref[k] + um;                                                  // any fp32 number near the max will do
@@ -441,13 +437,8 @@ __device__ __noinline__ HiIO<D, R, GRAD> subtile_hi(HiIO<D, R, GRAD> io, double*
         io.mref[k] = vm;
         io.sc[k] *= sc;
         K[k] -= shift;
-#ifdef KDOT_HI_EXACT_EXP
-        p0 = (float)exp2(u[k][0] - shift); p1 = (float)exp2(u[k][1] - shift);
-        p2 = (float)exp2(u[k][2] - shift); p3 = (float)exp2(u[k][3] - shift);
-#else
         p0 = ex2_approx(hi_pack(u[k][0] - shift)); p1 = ex2_approx(hi_pack(u[k][1] - shift));
         p2 = ex2_approx(hi_pack(u[k][2] - shift)); p3 = ex2_approx((float)(u[k][3] - shift));
-#endif
       }
       io.s[k].x += p0 + p2; io.s[k].y += p1 + p3;
       if (GRAD) {  // weights from the float64 argument, coordinate differences in fp32 (exact enough: they are O(cloud size))
