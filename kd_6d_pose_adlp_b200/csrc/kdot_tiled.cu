@@ -145,7 +145,8 @@ struct RowState {
   float2 nx, ny;    // (-px, -px), (-py, -py)
   float2 nm;        // (-mref, -mref)
   float mref;       // reference exponent of the running sums (may be stale by up to ~kTau)
-  float2 s;         // two partial exp sums
+  float2 s;         // two partial exp sums of the current 32-column block
+  float tot, comp;  // compensated (Kahan) total of the finished blocks, same scale; row sum = tot - comp (see row_fold)
   float2 gx, gy;    // sum e * (p_j - p_i), two partials each   (kGrad only)
 };
 
@@ -156,6 +157,21 @@ struct RowState {
 // with the exact max and re-bases the sums.  Values far BELOW the reference need no care (they underflow to the
 // correct negligible contribution).  Hot path per 4 pairs: 4 FADD2 + 2 FMUL2 + 4 FFMA2 + 2 FADD2 + 4 MUFU + 2 FADD2
 // + FADD + FSETP = 5.0 issue slots per pair against the SFU's 8 cycles per warp-wide ex2.
+// Row sums: fp32 accumulators span 32 columns only and are folded into a Kahan pair -- two running fp32 accumulators over a
+// 128-column row cost d/dx ~1e-5 in a solver that is otherwise exact (tools/rowsum_study.py).
+template <bool kGrad>
+__device__ __forceinline__ void row_fold(RowState<kGrad>& st) {
+  const float y = __fsub_rn(__fadd_rn(st.s.x, st.s.y), st.comp);
+  const float t = __fadd_rn(st.tot, y);
+  st.comp = __fsub_rn(__fsub_rn(t, st.tot), y);
+  st.tot = t;
+  st.s = make_float2(0.f, 0.f);
+}
+template <bool kGrad>
+__device__ __forceinline__ double row_lg2_sum(const RowState<kGrad>& st) {   // log2(tot - comp)
+  return lg2_sum_exact(st.tot) - (st.tot > 0.f ? (double)__fdiv_rn(st.comp, st.tot) * 1.4426950408889634 : 0.0);
+}
+
 template <bool kGrad>
 __device__ __forceinline__ void rows_vs_columns(RowState<kGrad> (&st)[kRows], const float* __restrict__ cx,
                                                 const float* __restrict__ cy, const float* __restrict__ ch, int c0,
@@ -163,7 +179,10 @@ __device__ __forceinline__ void rows_vs_columns(RowState<kGrad> (&st)[kRows], co
   const float2 coef2 = make_float2(coef, coef);
   const float big = exp2f(kTau);
 #pragma unroll 1
-  for (int j = c0; j < c1; j += 4) {
+  for (int jb = c0; jb < c1; jb += 32) {
+  const int je = min(jb + 32, c1);
+#pragma unroll 1
+  for (int j = jb; j < je; j += 4) {
     const float4 X = *reinterpret_cast<const float4*>(cx + j);
     const float4 Y = *reinterpret_cast<const float4*>(cy + j);
     const float4 H = *reinterpret_cast<const float4*>(ch + j);
@@ -202,6 +221,7 @@ __device__ __forceinline__ void rows_vs_columns(RowState<kGrad> (&st)[kRows], co
         const float vm = fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y));
         const float sc = ex2_approx(st[k].mref - vm);  // 0 for the first chunk (mref = -big)
         st[k].s.x *= sc; st[k].s.y *= sc;
+        st[k].tot *= sc; st[k].comp *= sc;
         if (kGrad) {
           st[k].gx.x *= sc; st[k].gx.y *= sc;
           st[k].gy.x *= sc; st[k].gy.y *= sc;
@@ -225,6 +245,9 @@ __device__ __forceinline__ void rows_vs_columns(RowState<kGrad> (&st)[kRows], co
         st[k].gy = __fadd2_rn(st[k].gy, pgy[k]);
       }
     }
+  }
+#pragma unroll
+  for (int k = 0; k < kRows; ++k) row_fold(st[k]);
   }
 }
 
@@ -295,6 +318,7 @@ __device__ __forceinline__ void rows_reset(RowState<kGrad> (&st)[kRows]) {
     st[k].mref = kNegBig;
     st[k].nm = make_float2(-kNegBig, -kNegBig);
     st[k].s = make_float2(0.f, 0.f);
+    st[k].tot = 0.f; st[k].comp = 0.f;
     st[k].gx = make_float2(0.f, 0.f);
     st[k].gy = make_float2(0.f, 0.f);
   }
@@ -421,7 +445,7 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
         }
         rows_vs_columns<false>(st, cx, cy, own ? hSc : hCc, c0, c1, rc.coef);
 #pragma unroll
-        for (int k = 0; k < kRows; ++k) lse[k] = (double)st[k].mref + lg2_sum_exact(st[k].s.x + st[k].s.y);
+        for (int k = 0; k < kRows; ++k) lse[k] = (double)st[k].mref + row_lg2_sum(st[k]);
       } else {
 #pragma unroll
         for (int k = 0; k < kRows; ++k) {
@@ -498,8 +522,8 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
           rows_vs_columns<true>(st, cx, cy, hSc, 0, Nq, rc.coef);
 #pragma unroll
           for (int k = 0; k < kRows; ++k) {
-            const float s = st[k].s.x + st[k].s.y;
-            S[k] = rc.scaled * ((double)st[k].mref + lg2_sum_exact(s) + cSX);
+            const float s = st[k].tot;
+            S[k] = rc.scaled * ((double)st[k].mref + row_lg2_sum(st[k]) + cSX);
             gSx[k] = (st[k].gx.x + st[k].gx.y) / s;
             gSy[k] = (st[k].gy.x + st[k].gy.y) / s;
           }
@@ -507,8 +531,8 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
           rows_vs_columns<true>(st, cx, cy, hCc, Nq, Pq, rc.coef);
 #pragma unroll
           for (int k = 0; k < kRows; ++k) {
-            const float s = st[k].s.x + st[k].s.y;
-            C[k] = rc.scaled * ((double)st[k].mref + lg2_sum_exact(s) + cCY);
+            const float s = st[k].tot;
+            C[k] = rc.scaled * ((double)st[k].mref + row_lg2_sum(st[k]) + cCY);
             gCx[k] = (st[k].gx.x + st[k].gx.y) / s;
             gCy[k] = (st[k].gy.x + st[k].gy.y) / s;
           }
@@ -571,7 +595,7 @@ __global__ void __launch_bounds__(kTiledThreads, KDOT_TILED_MINBLOCKS) kdot_tile
           }
           rows_vs_columns<false>(st, cx, cy, own ? hSc : hCc, c0, c1, rc.coef);
 #pragma unroll
-          for (int k = 0; k < kRows; ++k) lse[k] = (double)st[k].mref + lg2_sum_exact(st[k].s.x + st[k].s.y);
+          for (int k = 0; k < kRows; ++k) lse[k] = (double)st[k].mref + row_lg2_sum(st[k]);
         } else {
 #pragma unroll
           for (int k = 0; k < kRows; ++k) {

@@ -14,7 +14,7 @@ For every tensor three relative max-norm numbers are printed:
     ref32_vs_ref64                              (the reference formulation's own fp32 rounding noise)
 
 Measured on B200 (tools/accuracy_report.py, profiles/r02_accuracy.txt): d/dx 1e-6..1.1e-5 for the register kernel (ape
-shape), 8e-6..3e-5 for the CTA-resident kernel, 6e-6..1.4e-4 for the streaming kernel (``TOL_STREAM``).
+shape), 1.5e-6..1.5e-5 for the CTA-resident kernel, 3e-6..1.1e-4 for the streaming kernel (``TOL_STREAM``).
 """
 import numpy as np
 
