@@ -5,6 +5,7 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/${R}_pytest_gpu.txt
 python __graft_entry__.py --smoke 2>&1 | grep -v Warning | tail -6 | tee gpurun_out/${R}_smoke.txt
 python tools/accuracy_report.py --out gpurun_out/${R}_accuracy.json > gpurun_out/${R}_accuracy.txt 2>&1
+python tools/accuracy_stream_scan.py > gpurun_out/${R}_accuracy_stream16.txt 2>&1
 python tools/time_kd_pose_loss.py 64 > /dev/null 2>&1; cp gpurun_out/kd_pose_loss_timing.json gpurun_out/${R}_kd_pose_loss_timing.json
 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/${R}_bench_reference.json 2>/dev/null
 python bench.py > gpurun_out/${R}_bench_ape_b64.json 2> gpurun_out/${R}_bench.err
