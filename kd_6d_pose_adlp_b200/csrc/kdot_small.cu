@@ -511,9 +511,10 @@ __device__ __forceinline__ void fast_solve_rt(const FastCtx& c, int nch, int nro
 
 // The B slots of an image are spread over a thread-block cluster of `split` CTAs (B/split warps each) so that a
 // small batch still covers the whole chip with about one warp per SM sub-partition: the rounds are bound by the
-// per-sub-partition SFU / FP32 pipes, not by occupancy.  The cluster is only needed twice: a barrier before the
-// in-place normalisation (every CTA reads all slots for the bounding box) and the fixed-order sum over slots,
-// which rank 0 performs on values its peers wrote into its shared memory (DSMEM).
+// per-sub-partition SFU / FP32 pipes, not by occupancy.  The cluster is only needed twice, and never waited on before the
+// rounds: a split barrier around the in-place normalisation (arrive once this warp has read the raw points of all B
+// slots for the bounding box, wait -- long since complete -- before the normalised store at the end), and the fixed-order
+// sum over slots, which rank 0 performs on values its peers wrote into its shared memory (DSMEM).
 // ROLLED = false: per-chunk-count unrolled rounds, arguments held in registers (176 registers, one CTA per SM): lowest latency
 // when the batch gives every SM sub-partition at most one warp (ape_b64: 26.6 vs 28.9 us).  ROLLED = true: the rolled rounds
 // (120 registers, two CTAs per SM, L0-resident loops): 20 % more throughput once the grid exceeds one CTA per SM (1024 images:
