@@ -14,6 +14,11 @@ Two draw modes:
   (the test checks budgets, mask membership, distinctness and uniformity).
 
 ``targets`` are the reference's ``PoseAnnot`` objects (``libs/poses.py``) or anything with the attributes read below.
+
+Object counts: the reference's loop indexes ``bbox_trans.unsqueeze(0)`` -- a ``(1, 2, 3)`` tensor -- with the object index of
+every cell (``loss.py:184,253``), so it runs for ONE object per (cropped) image, which is what its data pipeline produces and
+what the golden fixtures hold.  The kernels and the packing below take up to 8 objects per image (one crop affine per image);
+that part has no reference run to compare with and is covered on the host side only (``tests/test_targets_host.py``).
 """
 from __future__ import annotations
 
