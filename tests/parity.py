@@ -22,8 +22,8 @@ TOL = 1e-4        # north-star tolerance, asserted against the fp64 oracle
 # Streaming kernel on clouds of several hundred points and more: 99.9 % of the d/dx entries are within 5e-6 of fp64 (row
 # sums are compensated per 32-column sub-tile since round 2; before that the fp32 running sums of 1000-term rows set the
 # error).  The max-norm is 3e-6..9e-5 over tools/accuracy_stream_scan.py's 16 cases; it reaches 1.1e-4 on a single
-# knife-edge cell of the dense 1360 x 1364 problem (a near-tie between two neighbours at eps = 1e-6 that moves by 1e-4 under
-# a 1e-7 perturbation of a potential; ref32 is at 1e-3 there) and may reach ~1.4e-4 on wide sparse clouds of more than 2048
+# knife-edge cell of the dense 1360 x 1364 problem (the EXACT gradient at that cell moves by 3e-4..7e-4 when the fp32 inputs
+# move by one ulp, tools/conditioning_study.py; ref32 is at 1e-3 there) and may reach ~1.4e-4 on wide sparse clouds of more than 2048
 # staged points (fp32 pair arguments below the float64 gate of the large batches).
 # Asserted: max-norm <= TOL_STREAM and 99.9 % quantile <= TOL / 2.
 TOL_STREAM = 1.5e-4
