@@ -14,19 +14,20 @@ For every tensor three relative max-norm numbers are printed:
     ref32_vs_ref64                              (the reference formulation's own fp32 rounding noise)
 
 Measured on B200 (tools/accuracy_report.py, profiles/r02_accuracy.txt): d/dx 1e-6..1.1e-5 for the register kernel (ape
-shape), 1.5e-6..1.5e-5 for the CTA-resident kernel, 3e-6..1.1e-4 for the streaming kernel (``TOL_STREAM``).
+shape), 1.5e-6..1.5e-5 for the CTA-resident kernel, 8e-7..4.4e-5 for the streaming kernel over the cases of the suite.
 """
 import numpy as np
 
 TOL = 1e-4        # north-star tolerance, asserted against the fp64 oracle
-# Streaming kernel on clouds of several hundred points and more: 99.9 % of the d/dx entries are within 5e-6 of fp64 (row
-# sums are compensated per 32-column sub-tile since round 2; before that the fp32 running sums of 1000-term rows set the
-# error).  The max-norm is 3e-6..9e-5 over tools/accuracy_stream_scan.py's 16 cases; it reaches 1.1e-4 on a single
-# knife-edge cell of the dense 1360 x 1364 problem (the EXACT gradient at that cell moves by 3e-4..7e-4 when the fp32 inputs
-# move by one ulp, tools/conditioning_study.py; ref32 is at 1e-3 there) and may reach ~1.4e-4 on wide sparse clouds of more than 2048
-# staged points (fp32 pair arguments below the float64 gate of the large batches, DESIGN.md section 3).
+# Streaming kernel.  Until the row sums were compensated (round 2: fp32 accumulators span 32 columns and are folded into a
+# Kahan pair) its d/dx sat at 2e-5..3e-4 and this constant was 2e-4; now every case of the suite is within 4.4e-5 of fp64
+# (1e-6..3e-5 mostly; 3500 x 3400: 4.4e-5) and the bar is the north-star's for this family too, plus a quantile clause.
+# The one KNOWN case above 1e-4 is not in the suite: tools/accuracy_report.py's dense 1360 x 1364 problem (seed 5) has one
+# cell at 1.1e-4 whose EXACT gradient moves by 3e-4..7e-4 when the fp32 inputs move by one ulp (tools/conditioning_study.py);
+# wide sparse clouds of more than 2048 staged points keep fp32 pair arguments up to a centred offset magnitude of 4096
+# log2-units (DESIGN.md section 3) and are not covered by a case either.
 # Asserted: max-norm <= TOL_STREAM and 99.9 % quantile <= TOL / 2.
-TOL_STREAM = 1.5e-4
+TOL_STREAM = TOL
 
 
 FLOOR = 1e-20    # a tensor whose exact values are below this (Gaussian-kernel gradients at D = 16, blur = 0.01 underflow
